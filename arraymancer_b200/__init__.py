@@ -1,0 +1,13 @@
+"""arraymancer_b200 — B200-native (sm_100a) drop-in for Arraymancer's dense-contraction hot path:
+`gemm_strided` / `CudaTensor *` for float32, float64, int32, int64 and the im2col+GEMM conv2d
+forward/backward (as a fused implicit GEMM).  The arithmetic lives in
+libarraymancer_b200.so (C ABI: include/am_b200.h); this package is the thin host-side mirror of
+the reference's operator interface.  There is no CPU fallback."""
+from . import _capi
+from ._capi import AmError, F32_AUTO, F32_SIMT, F32_TC, F32_TC_1CTA, set_f32_path, version
+from .cuda_tensor import CudaTensor, cuda, cublas_gemm, gemm, gemm_strided, matmul
+from .nn_primitives import conv2d, conv2d_backward, conv_out_dims
+
+__all__ = ["AmError", "CudaTensor", "cuda", "cublas_gemm", "gemm", "gemm_strided", "matmul", "conv2d",
+           "conv2d_backward", "conv_out_dims", "set_f32_path", "version", "F32_AUTO", "F32_SIMT", "F32_TC",
+           "F32_TC_1CTA"]

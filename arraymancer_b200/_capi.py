@@ -1,0 +1,112 @@
+"""ctypes binding of libarraymancer_b200.so — the C-ABI declared in include/am_b200.h.
+
+The product path has NO fallback: if the CUDA library is missing or a call fails, this module
+raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarraymancer_b200.so")
+
+AM_OK, AM_ERR_INVALID, AM_ERR_CUDA, AM_ERR_UNSUPPORTED, AM_ERR_NONCONTIGUOUS = range(5)
+F32_AUTO, F32_SIMT, F32_TC, F32_TC_1CTA = range(4)
+
+SUFFIXES = ("f32", "f64", "i32", "i64")
+CTYPE = {"f32": ctypes.c_float, "f64": ctypes.c_double, "i32": ctypes.c_int32, "i64": ctypes.c_int64}
+
+# every symbol include/am_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path",
+     "am_cublas_gemm_f32", "am_cublas_gemm_f64", "am_pack_f32_a", "am_pack_f32_b", "am_repack_f32_a",
+     "am_repack_f32_b", "am_gemm_packed_f32", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench"]
+    + [f"am_gemm_strided_{s}" for s in SUFFIXES]
+    + [f"am_host_gemm_strided_{s}" for s in SUFFIXES]
+    + [f"am_conv2d_forward_{s}" for s in SUFFIXES]
+    + [f"am_conv2d_backward_{s}" for s in SUFFIXES]
+)
+
+
+class ConvDesc(ctypes.Structure):
+    """am_conv2d_desc"""
+    _fields_ = [(n, ctypes.c_int64) for n in
+                ("N", "C", "H", "W", "Cout", "kH", "kW", "padH", "padW", "strideH", "strideW", "dilH", "dilW")]
+
+
+class AmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"arraymancer_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C arraymancer_b200/csrc`.  There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    i64, p, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+    L.am_version.restype = ctypes.c_char_p
+    L.am_last_error.restype = ctypes.c_char_p
+    L.am_device_info.argtypes = [ctypes.POINTER(ci)] * 3
+    L.am_set_f32_path.argtypes = [ci]
+    L.am_kernel_launch_count.restype = i64
+    L.am_microbench.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    L.am_conv2d_out_dims.argtypes = [ctypes.POINTER(ConvDesc), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    for s in SUFFIXES:
+        ct = CTYPE[s]
+        getattr(L, f"am_gemm_strided_{s}").argtypes = [p, i64, i64, i64, ct, p, i64, i64, p, i64, i64, ct, p, i64, i64]
+        getattr(L, f"am_host_gemm_strided_{s}").argtypes = [i64, i64, i64, ct, p, i64, i64, p, i64, i64, ct, p, i64, i64]
+        getattr(L, f"am_conv2d_forward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p]
+        getattr(L, f"am_conv2d_backward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, p]
+    f = ctypes.c_float
+    L.am_pack_f32_a.argtypes = [p, i64, i64, p, i64, i64, ctypes.POINTER(p)]
+    L.am_pack_f32_b.argtypes = [p, i64, i64, p, i64, i64, ctypes.POINTER(p)]
+    L.am_repack_f32_a.argtypes = [p, p, p, i64, i64]
+    L.am_repack_f32_b.argtypes = [p, p, p, i64, i64]
+    L.am_gemm_packed_f32.argtypes = [p, f, p, p, f, p, i64, i64]
+    L.am_packed_free_f32.argtypes = [p]
+    for s in ("f32", "f64"):
+        ct = CTYPE[s]
+        getattr(L, f"am_cublas_gemm_{s}").argtypes = [p, ci, ci, i64, i64, i64, ct, p, i64, p, i64, ct, p, i64]
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    """Mirror of nimcuda's `check`: turn a non-zero status into an exception."""
+    if code != AM_OK:
+        raise AmError(code, lib().am_last_error().decode(errors="replace"))
+
+
+def version() -> str:
+    return lib().am_version().decode()
+
+
+def device_info():
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib().am_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def set_f32_path(path: int) -> None:
+    check(lib().am_set_f32_path(path))
+
+
+def kernel_launch_count() -> int:
+    return int(lib().am_kernel_launch_count())
+
+
+def microbench(which: int) -> float:
+    out = ctypes.c_double()
+    check(lib().am_microbench(which, ctypes.byref(out)))
+    return out.value

@@ -1,0 +1,283 @@
+// extern "C" entry points of libarraymancer_b200.so (declared in include/am_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "am_common.cuh"
+#include "gemm_dispatch.h"
+
+namespace am {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_last_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return AM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ per-device workspace
+struct WsEntry { void* p = nullptr; size_t bytes = 0; };
+static std::mutex g_ws_mu;
+static WsEntry g_ws[16][kWsNumSlots];
+static int g_sm[16] = {0};
+void conv_tables_invalidate();
+
+int workspace(int slot, size_t bytes, void** out) {
+  int dev = 0;
+  AM_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || slot < 0 || slot >= kWsNumSlots) { set_last_error("workspace: bad slot"); return AM_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  WsEntry& e = g_ws[dev][slot];
+  if (e.bytes < bytes || !e.p) {
+    if (e.p) {
+      // the old block may still be in use by enqueued work: cudaFree synchronises the device first
+      AM_CUDA_TRY(cudaFree(e.p));
+      e.p = nullptr; e.bytes = 0;
+      if (slot == kWsConvTab) conv_tables_invalidate();
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    want = (want + (want >> 3) + 255) & ~(size_t)255;          // 12.5% slack against regrowth
+    AM_CUDA_TRY(cudaMalloc(&e.p, want));
+    e.bytes = want;
+  }
+  *out = e.p;
+  return AM_OK;
+}
+void workspace_release_all() {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 16; d++)
+    for (int s = 0; s < kWsNumSlots; s++)
+      if (g_ws[d][s].p) {
+        cudaSetDevice(d);
+        cudaFree(g_ws[d][s].p);
+        g_ws[d][s] = WsEntry{};
+      }
+  cudaSetDevice(cur);
+  conv_tables_invalidate();
+}
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (!g_sm[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sm[dev] = n;
+  }
+  return g_sm[dev];
+}
+
+static std::atomic<int> g_f32_path{AM_F32_AUTO};
+
+template <class T>
+static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, const T* B, T* C) {
+  if (M < 0 || N < 0 || K < 0) { set_last_error("gemm_strided: negative dimension"); return AM_ERR_INVALID; }
+  if (M == 0 || N == 0 || K == 0) return -1;   // nothing to do (K == 0 leaves C untouched, gemm.nim:203)
+  if (!A || !B || !C) { set_last_error("gemm_strided: null operand pointer"); return AM_ERR_INVALID; }
+  return AM_OK;
+}
+
+// f32: tcgen05 3xTF32 when the shape fills tensor tiles, exact FFMA kernel otherwise.
+static int gemm_f32_dispatch(cudaStream_t st, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                             int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta,
+                             float* C, int64_t rsC, int64_t csC) {
+  const int path = g_f32_path.load();
+  if (path == AM_F32_TC) return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  if (path == AM_F32_TC_1CTA) return gemm_f32_tc(st, 1, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  if (path == AM_F32_AUTO && gemm_f32_tc_available()) {
+    // tensor tiles are 256x512 (pair) / 128x256: worth it once the output fills a wave of them and K
+    // amortises the split/pack pre-pass (an extra pass over A and B).
+    const double flops = 2.0 * (double)M * (double)N * (double)K;
+    if (M >= 512 && N >= 512 && K >= 256 && flops >= 2.0e10)
+      return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  }
+  return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+}
+
+// host-buffer GEMM: what `a.cuda * b.cuda` then `.cpu` does (init_cuda.nim:23-59).
+template <class T, class F>
+static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
+                     int64_t csA, const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) {
+  int rc = check_gemm_args(M, N, K, A, B, C);
+  if (rc == -1) return AM_OK;
+  if (rc) return rc;
+  // Bounding extents of each (possibly negatively strided) view, in elements.
+  auto extent = [](int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t* lo, int64_t* hi) {
+    int64_t a = (r - 1) * rs, b = (c - 1) * cs;
+    *lo = (a < 0 ? a : 0) + (b < 0 ? b : 0);
+    *hi = (a > 0 ? a : 0) + (b > 0 ? b : 0);
+  };
+  int64_t loA, hiA, loB, hiB, loC, hiC;
+  extent(M, K, rsA, csA, &loA, &hiA);
+  extent(K, N, rsB, csB, &loB, &hiB);
+  extent(M, N, rsC, csC, &loC, &hiC);
+  const size_t nA = (size_t)(hiA - loA + 1), nB = (size_t)(hiB - loB + 1), nC = (size_t)(hiC - loC + 1);
+  cudaStream_t st = nullptr;
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  T *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  int status = AM_OK;
+  do {
+    if (cudaMallocAsync(&dA, nA * sizeof(T), st) != cudaSuccess || cudaMallocAsync(&dB, nB * sizeof(T), st) != cudaSuccess ||
+        cudaMallocAsync(&dC, nC * sizeof(T), st) != cudaSuccess) { status = cuda_fail(cudaGetLastError(), "cudaMallocAsync"); break; }
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dA, A + loA, nA * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(dB, B + loB, nB * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess) { status = cuda_fail(e, "H2D"); break; }
+    if (beta != T(0) || nC != (size_t)(M * N)) {   // C is read, or the view has gaps that must survive the D2H copy
+      if ((e = cudaMemcpyAsync(dC, C + loC, nC * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess) { status = cuda_fail(e, "H2D C"); break; }
+    }
+    status = device_gemm(st, M, N, K, alpha, dA - loA, rsA, csA, dB - loB, rsB, csB, beta, dC - loC, rsC, csC);
+    if (status) break;
+    if ((e = cudaMemcpyAsync(C + loC, dC, nC * sizeof(T), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { status = cuda_fail(e, "sync"); break; }
+  } while (0);
+  if (dA) cudaFreeAsync(dA, st);
+  if (dB) cudaFreeAsync(dB, st);
+  if (dC) cudaFreeAsync(dC, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return status;
+}
+
+}  // namespace am
+
+using namespace am;
+
+extern "C" {
+
+const char* am_version(void) { return "arraymancer_b200 0.1 (sm_100a)"; }
+const char* am_last_error(void) { return g_err; }
+
+int am_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  AM_CUDA_TRY(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  AM_CUDA_TRY(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  AM_CUDA_TRY(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  AM_CUDA_TRY(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sms) *sms = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return AM_OK;
+}
+
+int am_shutdown(void) {
+  workspace_release_all();
+  return AM_OK;
+}
+
+int am_set_f32_path(int path) {
+  if (path < AM_F32_AUTO || path > AM_F32_TC_1CTA) { set_last_error("am_set_f32_path: bad selector"); return AM_ERR_INVALID; }
+  g_f32_path.store(path);
+  return AM_OK;
+}
+int am_get_f32_path(void) { return g_f32_path.load(); }
+
+int64_t am_kernel_launch_count(void) { return g_launch_count.load(); }
+int am_microbench(int which, double* tops) { return microbench(which, tops); }
+
+int am_gemm_strided_f32(am_stream_t s, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA,
+                        int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C, int64_t rsC,
+                        int64_t csC) {
+  int rc = check_gemm_args(M, N, K, A, B, C);
+  if (rc == -1) return AM_OK;
+  if (rc) return rc;
+  return gemm_f32_dispatch((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+}
+
+#define DEF_GEMM_SIMT(SUF, T)                                                                                  \
+  int am_gemm_strided_##SUF(am_stream_t s, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,   \
+                            int64_t csA, const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC,       \
+                            int64_t csC) {                                                                      \
+    int rc = check_gemm_args(M, N, K, A, B, C);                                                                 \
+    if (rc == -1) return AM_OK;                                                                                 \
+    if (rc) return rc;                                                                                          \
+    return gemm_simt<T>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);          \
+  }
+DEF_GEMM_SIMT(f64, double)
+DEF_GEMM_SIMT(i32, int32_t)
+DEF_GEMM_SIMT(i64, int64_t)
+
+int am_pack_f32_a(am_stream_t s, int64_t M, int64_t K, const float* A, int64_t rsA, int64_t csA, am_packed_f32** out) {
+  return pack_f32((cudaStream_t)s, M, K, A, rsA, csA, (void**)out);
+}
+int am_pack_f32_b(am_stream_t s, int64_t K, int64_t N, const float* B, int64_t rsB, int64_t csB, am_packed_f32** out) {
+  return pack_f32((cudaStream_t)s, N, K, B, csB, rsB, (void**)out);
+}
+int am_repack_f32_a(am_stream_t s, am_packed_f32* h, const float* A, int64_t rsA, int64_t csA) {
+  return repack_f32((cudaStream_t)s, h, A, rsA, csA);
+}
+int am_repack_f32_b(am_stream_t s, am_packed_f32* h, const float* B, int64_t rsB, int64_t csB) {
+  return repack_f32((cudaStream_t)s, h, B, csB, rsB);
+}
+int am_gemm_packed_f32(am_stream_t s, float alpha, const am_packed_f32* A, const am_packed_f32* B, float beta,
+                       float* C, int64_t rsC, int64_t csC) {
+  return gemm_packed_f32((cudaStream_t)s, alpha, A, B, beta, C, rsC, csC);
+}
+int am_packed_free_f32(am_packed_f32* h) { return packed_free_f32(h); }
+
+// cublas_gemm adapter (cublas.nim:142-170): column-major, op N -> (rs=1, cs=ld), op T -> (rs=ld, cs=1)
+#define DEF_CUBLAS(SUF, T)                                                                                     \
+  int am_cublas_gemm_##SUF(am_stream_t s, int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha,     \
+                           const T* A, int64_t lda, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {       \
+    if ((transa != 0 && transa != 1) || (transb != 0 && transb != 1)) {                                         \
+      set_last_error("cublas_gemm: only CUBLAS_OP_N (0) / CUBLAS_OP_T (1) are supported");                      \
+      return AM_ERR_INVALID;                                                                                    \
+    }                                                                                                           \
+    const int64_t rowsA = transa ? k : m, rowsB = transb ? n : k;                                               \
+    if (lda < (rowsA > 1 ? rowsA : 1) || ldb < (rowsB > 1 ? rowsB : 1) || ldc < (m > 1 ? m : 1)) {              \
+      set_last_error("cublas_gemm: leading dimension smaller than the matrix rows");                            \
+      return AM_ERR_NONCONTIGUOUS;                                                                              \
+    }                                                                                                           \
+    return am_gemm_strided_##SUF(s, m, n, k, alpha, A, transa ? lda : 1, transa ? 1 : lda, B, transb ? ldb : 1, \
+                                 transb ? 1 : ldb, beta, C, 1, ldc);                                            \
+  }
+DEF_CUBLAS(f32, float)
+DEF_CUBLAS(f64, double)
+
+int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
+  if (!d || d->strideH <= 0 || d->strideW <= 0 || d->dilH <= 0 || d->dilW <= 0) { set_last_error("conv2d_out_dims: bad descriptor"); return AM_ERR_INVALID; }
+  if (Ho) *Ho = (d->H + 2 * d->padH - (d->dilH * (d->kH - 1) + 1)) / d->strideH + 1;
+  if (Wo) *Wo = (d->W + 2 * d->padW - (d->dilW * (d->kW - 1) + 1)) / d->strideW + 1;
+  return AM_OK;
+}
+
+#define DEF_CONV(SUF, T)                                                                                       \
+  int am_conv2d_forward_##SUF(am_stream_t s, const am_conv2d_desc* d, const T* in, const T* k, const T* b,      \
+                              T* out) {                                                                         \
+    if (!d) { set_last_error("conv2d_forward: null descriptor"); return AM_ERR_INVALID; }                      \
+    return conv2d_forward<T>((cudaStream_t)s, *d, in, k, b, out);                                               \
+  }                                                                                                             \
+  int am_conv2d_backward_##SUF(am_stream_t s, const am_conv2d_desc* d, const T* in, const T* k, const T* go,    \
+                               T* gi, T* gk, T* gb) {                                                           \
+    if (!d) { set_last_error("conv2d_backward: null descriptor"); return AM_ERR_INVALID; }                     \
+    return conv2d_backward<T>((cudaStream_t)s, *d, in, k, go, gi, gk, gb);                                      \
+  }
+DEF_CONV(f32, float)
+DEF_CONV(f64, double)
+DEF_CONV(i32, int32_t)
+DEF_CONV(i64, int64_t)
+
+#define DEF_HOST(SUF, T)                                                                                       \
+  int am_host_gemm_strided_##SUF(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA, \
+                                 const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) { \
+    return host_gemm<T>(                                                                                        \
+        [](cudaStream_t st, int64_t m, int64_t n, int64_t k, T al, const T* a, int64_t ra, int64_t ca,          \
+           const T* b, int64_t rb, int64_t cb, T be, T* c, int64_t rc_, int64_t cc) {                           \
+          return am_gemm_strided_##SUF((am_stream_t)st, m, n, k, al, a, ra, ca, b, rb, cb, be, c, rc_, cc);     \
+        },                                                                                                      \
+        M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);                                           \
+  }
+DEF_HOST(f32, float)
+DEF_HOST(f64, double)
+DEF_HOST(i32, int32_t)
+DEF_HOST(i64, int64_t)
+
+}  // extern "C"

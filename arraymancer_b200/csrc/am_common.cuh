@@ -1,0 +1,78 @@
+// Shared helpers for the B200 dense-contraction kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+#include "../../include/am_b200.h"
+
+namespace am {
+
+// ---- status / last error (no exceptions or aborts cross the C ABI) -------------------------
+void set_last_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);   // records + returns AM_ERR_CUDA
+
+#define AM_CUDA_TRY(expr)                                  \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return am::cuda_fail(_e, #expr); \
+  } while (0)
+
+// ---- per-device workspace cache (the shim may keep one, freed by am_shutdown) --
+// slot ids
+enum WsSlot : int { kWsSplitA = 0, kWsSplitB = 1, kWsConv = 2, kWsConvTab = 3, kWsMisc = 4, kWsNumSlots = 8 };
+// returns device pointer valid until the next workspace() call for the same (device,slot) with a larger size
+int workspace(int slot, size_t bytes, void** out);
+void workspace_release_all();
+int sm_count();
+
+// ---- arithmetic that matches the reference's element semantics -----------------------------
+// integers wrap mod 2^n: do everything in the unsigned type.
+template <class T> struct UnsignedOf { using type = T; };
+template <> struct UnsignedOf<int32_t> { using type = uint32_t; };
+template <> struct UnsignedOf<int64_t> { using type = uint64_t; };
+
+template <class T>
+__device__ __forceinline__ T mac(T a, T b, T acc) {
+  if constexpr (std::is_same<T, float>::value) return fmaf(a, b, acc);
+  else if constexpr (std::is_same<T, double>::value) return fma(a, b, acc);
+  else {
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)acc + (U)a * (U)b);
+  }
+}
+template <class T>
+__device__ __forceinline__ T mul_nocontract(T a, T b) {
+  if constexpr (std::is_same<T, float>::value) return __fmul_rn(a, b);
+  else if constexpr (std::is_same<T, double>::value) return __dmul_rn(a, b);
+  else {
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)a * (U)b);
+  }
+}
+template <class T>
+__device__ __forceinline__ T add_nocontract(T a, T b) {
+  if constexpr (std::is_same<T, float>::value) return __fadd_rn(a, b);
+  else if constexpr (std::is_same<T, double>::value) return __dadd_rn(a, b);
+  else {
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)a + (U)b);
+  }
+}
+
+// Epilogue of gemm_ukernel_generic.nim:96-125 applied once to the full-K sum:
+//   beta == 0 : C = (alpha == 1 ? AB : alpha*AB)          (never reads C)
+//   else      : C = C*beta ; C += (alpha == 1 ? AB : alpha*AB)   (separately rounded)
+template <class T>
+__device__ __forceinline__ T epilogue_value(T alpha, T ab, T beta, T cold) {
+  T v = (alpha == T(1)) ? ab : mul_nocontract<T>(alpha, ab);
+  if (beta == T(0)) return v;
+  T c = (beta == T(1)) ? cold : mul_nocontract<T>(cold, beta);
+  return add_nocontract<T>(c, v);
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+static inline int64_t iabs64(int64_t a) { return a < 0 ? -a : a; }
+
+}  // namespace am

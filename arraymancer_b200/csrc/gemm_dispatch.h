@@ -1,0 +1,43 @@
+// Internal declarations shared by the translation units of libarraymancer_b200.so.
+#pragma once
+#include <atomic>
+#include <cmath>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/am_b200.h"
+
+namespace am {
+
+extern std::atomic<int64_t> g_launch_count;
+
+// gemm_simt.cu — strided SIMT GEMM, any layout
+template <class T>
+int gemm_simt(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA,
+              const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC);
+
+// gemm_f32_tc.cu — tcgen05 3xTF32 GEMM (split/pack pre-pass + TMA/UMMA mainloop)
+// cta_group: 1 or 2
+int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
+                int64_t rsC, int64_t csC);
+bool gemm_f32_tc_available();
+// pre-packed operands (two tf32 planes, K-major): pack once, multiply many
+int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, void** handle);
+int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride);
+int packed_free_f32(void* handle);
+int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB, float beta, float* C, int64_t rsC,
+                    int64_t csC);
+
+// conv.cu
+template <class T>
+int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
+                   T* output);
+template <class T>
+int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel,
+                    const T* grad_output, T* grad_input, T* grad_kernel, T* grad_bias);
+
+// peaks.cu
+int microbench(int which, double* tops);
+
+}  // namespace am

@@ -1,0 +1,411 @@
+// float32 GEMM on the 5th-gen tensor cores with a 3xTF32 split that keeps fp32 accuracy.
+//
+//   C = alpha * A*B + beta*C,  A = Ahi + Alo (+ ~2^-22 |A|),  B = Bhi + Blo
+//   A*B ~= Alo*Bhi + Ahi*Blo + Ahi*Bhi   — three kind::tf32 UMMAs accumulating in fp32 in TMEM.
+//
+// Two kernels:
+//  1. split_pack_kernel — the "packing" pass (role of laser's pack_A_mc_kc / pack_B_kc_nc,
+//     gemm_packing.nim:24-99): reads an operand through ANY (row, col) stride pair — negative,
+//     zero, transposed — and writes two K-major planes (hi, lo), tf32-rounded, zero padded to
+//     tile multiples.  O(MK + KN) bytes, ~3 % of a 16384^3 GEMM.
+//  2. gemm_tf32x3_kernel<CG, BK> — warp-specialised mainloop: warp 0 = TMA producer
+//     (cp.async.bulk.tensor, 128B/64B-swizzled K-major tiles, mbarrier ring), warp 1 = UMMA issuer
+//     (one elected lane, tcgen05.mma kind::tf32, accumulators in TMEM), warps 2-5 = epilogue
+//     (tcgen05.ld -> alpha/beta -> strided global stores; lanes run along C's unit-stride dim).
+//     CG = 2: CTA pair (cta_group::2), 256x512 output tile per pair = all 512 TMEM columns of both
+//     SMs; each CTA stages its 128 rows of A and half of B, halving smem/L2 operand traffic.
+//     CG = 1: single CTA, 128x256 tile (bring-up / comparison).
+//
+// Replaces the cuBLAS call behind CudaTensor `*` (tensor/backend/cublas.nim:142-170) and the
+// float branch of gemm (tensor/operators_blas_l2l3.nim:58-71) for large shapes.
+#include <cuda.h>
+#include <cstdlib>
+
+#include "am_common.cuh"
+#include "gemm_dispatch.h"
+#include "ptx_sm100.cuh"
+
+namespace am {
+
+// ------------------------------------------------------------------ split / pack pre-pass
+// out planes: [Rpad][Kpad] row-major (K contiguous).  (r, k) of X at X[r*r_stride + k*k_stride].
+__global__ void __launch_bounds__(256)
+split_pack_kernel(const float* __restrict__ X, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride,
+                  float* __restrict__ hi, float* __restrict__ lo, int64_t Kpad, int k_fast) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t k0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  float v[4];
+  if (k_fast) {
+    const int64_t k = k0 + tx;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = r0 + ty + 8 * i;
+      v[i] = (r < R && k < K) ? X[r * r_stride + k * k_stride] : 0.f;
+    }
+  } else {   // rows are the fast source dimension: read along r, transpose through smem
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = r0 + tx, k = k0 + ty + 8 * i;
+      tile[ty + 8 * i][tx] = (r < R && k < K) ? X[r * r_stride + k * k_stride] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = tile[tx][ty + 8 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int64_t r = r0 + ty + 8 * i;
+    const float x = v[i];
+    float h, l;
+    if (isfinite(x)) { h = ptx::to_tf32_rna(x); l = ptx::to_tf32_rna(x - h); if (!isfinite(h)) { h = x; l = 0.f; } }
+    else { h = x; l = 0.f; }
+    const int64_t o = r * Kpad + k0 + tx;
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+// ------------------------------------------------------------------ mainloop
+template <int CG, int BK>
+struct TcCfg {
+  static constexpr int ROWS_A = 128;                 // A rows staged per CTA (= UMMA M per CTA)
+  static constexpr int ROWS_B = 256;                 // B rows staged per CTA
+  static constexpr int TILE_M = 128 * CG;            // output tile of the CTA (pair)
+  static constexpr int TILE_N = 256 * CG;
+  static constexpr int NHALF = CG;                   // accumulator halves of 256 columns
+  static constexpr int TMEM_COLS = 256 * CG;
+  static constexpr int ROW_BYTES = BK * 4;           // 128 (SW128) or 64 (SW64)
+  static constexpr int SBO = 8 * ROW_BYTES;
+  static constexpr int BOX_BYTES = 128 * ROW_BYTES;  // one TMA box: 128 rows x BK floats
+  static constexpr int A_BYTES = BOX_BYTES;          // per plane
+  static constexpr int B_BYTES = 2 * BOX_BYTES;      // per plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // 2 @ BK=32, 4 @ BK=16
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int NTHREADS = 192;
+};
+
+struct TcArgs {
+  int64_t M, N;            // logical output extent (rows = TMEM lanes, cols = TMEM columns)
+  int kblocks;             // Kpad / BK
+  int tiles_m, tiles_n;
+  float* C; int64_t rsC, csC;
+  float alpha, beta;
+};
+
+template <int CG, int BK>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                   const TcArgs p) {
+  using Cfg = TcCfg<CG, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;      // SW128 needs 1024-B alignment
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  auto stage_base = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
+  // stage layout: [A_hi | A_lo | B_hi (256 rows) | B_lo (256 rows)]
+  constexpr uint32_t OFF_AHI = 0, OFF_ALO = Cfg::A_BYTES, OFF_BHI = 2 * Cfg::A_BYTES, OFF_BLO = 2 * Cfg::A_BYTES + Cfg::B_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = ptx::lane_id();
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  // tile of this CTA (pair): grouped rasterisation, 8 M-tiles per group, for L2 reuse of B panels
+  const int tile = (int)(blockIdx.x / CG);
+  constexpr int GROUP = 8;
+  const int group_size = GROUP * p.tiles_n;
+  const int g = tile / group_size;
+  const int first_m = g * GROUP;
+  const int gm = (p.tiles_m - first_m < GROUP) ? (p.tiles_m - first_m) : GROUP;
+  const int tm = first_m + (tile % group_size) % gm;
+  const int tn = (tile % group_size) / gm;
+  const int row0 = tm * Cfg::TILE_M + (int)cta_rank * 128;     // first A row staged by this CTA
+  const int col0 = tn * Cfg::TILE_N;                           // first B row (output column) of the tile
+
+  if (CG == 2) ptx::cluster_sync();    // peer CTA must be resident before any remote barrier traffic
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tmAhi); ptx::prefetch_tensormap(&tmAlo);
+    ptx::prefetch_tensormap(&tmBhi); ptx::prefetch_tensormap(&tmBlo);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < Cfg::STAGES; s++) {
+      ptx::mbar_init(full_bar(s), CG);      // one arrival per producer CTA (both arrive on the leader's)
+      ptx::mbar_init(empty_bar(s), 1);      // one tcgen05.commit (multicast to both CTAs when CG == 2)
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int nkb = p.kblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane, in every CTA) =====================
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sb = stage_base(s);
+        const int kc = kb * BK;
+        if constexpr (CG == 1) {
+          const uint32_t fb = full_bar(s);
+          ptx::mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+          ptx::tma_load_2d(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+          ptx::tma_load_2d(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+          ptx::tma_load_2d(sb + OFF_BHI, &tmBhi, fb, kc, col0);
+          ptx::tma_load_2d(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, col0 + 128);
+          ptx::tma_load_2d(sb + OFF_BLO, &tmBlo, fb, kc, col0);
+          ptx::tma_load_2d(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, col0 + 128);
+        } else {
+          // all transaction bytes of both CTAs land on the LEADER's full barrier
+          const uint32_t fb = ptx::mapa(full_bar(s), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+          else ptx::mbar_arrive_cluster(fb);
+          // accumulator half h covers output columns col0 + h*256 .. +255; this CTA supplies the
+          // B rows [rank*128, rank*128+128) of each half
+          const int b0 = col0 + (int)cta_rank * 128;
+          ptx::tma_load_2d_pair(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+          ptx::tma_load_2d_pair(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+          ptx::tma_load_2d_pair(sb + OFF_BHI, &tmBhi, fb, kc, b0);
+          ptx::tma_load_2d_pair(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, b0 + 256);
+          ptx::tma_load_2d_pair(sb + OFF_BLO, &tmBlo, fb, kc, b0);
+          ptx::tma_load_2d_pair(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, b0 + 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer (leader CTA only, one elected lane) =====================
+    if (leader && ptx::elect_one()) {
+      const uint64_t dhi = ptx::umma_desc_hi(Cfg::SBO, Cfg::ROW_BYTES);
+      const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        const uint32_t sb = stage_base(s);
+#pragma unroll
+        for (int k8 = 0; k8 < BK / 8; k8++) {
+          const uint32_t koff = k8 * 32;                         // 8 tf32 = 32 bytes along K inside the swizzle atom
+          const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff);
+          const uint64_t a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
+#pragma unroll
+          for (int h = 0; h < Cfg::NHALF; h++) {
+            // CG == 1: one 256-row B operand.  CG == 2: half h = this CTA's 128-row block h (peer supplies the rest)
+            const uint32_t boff = (CG == 2) ? (uint32_t)h * Cfg::BOX_BYTES : 0u;
+            const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + boff + koff);
+            const uint64_t b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + boff + koff);
+            const uint32_t d = tmem_base + (uint32_t)h * 256u;
+            const uint32_t first = (kb == 0 && k8 == 0) ? 0u : 1u;
+            ptx::umma_tf32<CG>(d, a_lo, b_hi, idesc, first);     // small terms first
+            ptx::umma_tf32<CG>(d, a_hi, b_lo, idesc, 1u);
+            ptx::umma_tf32<CG>(d, a_hi, b_hi, idesc, 1u);
+          }
+        }
+        ptx::umma_commit<CG>(empty_bar(s));                      // frees the stage in both CTAs once the MMAs retire
+        if (kb == nkb - 1) ptx::umma_commit<CG>(tmem_full_bar);  // accumulators complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5: TMEM -> registers -> global =====================
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int q = warp & 3;                                      // TMEM lane quarter this warp may access
+    const int64_t m = (int64_t)row0 + q * 32 + (int)lane;
+    const bool m_ok = m < p.M;
+    float* crow = p.C + m * p.rsC;
+    const float alpha = p.alpha, beta = p.beta;
+    for (int c = 0; c < Cfg::TMEM_COLS; c += 32) {
+      if ((int64_t)col0 + c >= p.N) break;                       // warp-uniform
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+      if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int64_t n = (int64_t)col0 + c + j;
+          if (n < p.N) {
+            float* pc = crow + n * p.csC;
+            const float cold = (beta != 0.f) ? *pc : 0.f;
+            *pc = epilogue_value<float>(alpha, __uint_as_float(r[j]), beta, cold);
+          }
+        }
+      }
+    }
+  }
+
+  // teardown: nobody may leave (or free TMEM) while the pair still has traffic in flight
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_TmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+static PFN_TmapEncodeTiled g_encode = nullptr;
+static int g_tc_state = 0;   // 0 unknown, 1 available, -1 unavailable
+
+bool gemm_f32_tc_available() {
+  if (g_tc_state == 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      g_tc_state = -1; return false;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (major != 10 || cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+      g_tc_state = -1; return false;
+    }
+    g_encode = (PFN_TmapEncodeTiled)fn;
+    g_tc_state = 1;
+  }
+  return g_tc_state == 1;
+}
+
+static int make_tmap(CUtensorMap* tm, float* base, int64_t rows, int64_t kpad, int bk) {
+  cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kpad * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)bk, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return AM_ERR_CUDA; }
+  return AM_OK;
+}
+
+template <int CG, int BK>
+static int launch_tc(cudaStream_t st, const CUtensorMap* tms, const TcArgs& args) {
+  using Cfg = TcCfg<CG, BK>;
+  auto kern = gemm_tf32x3_kernel<CG, BK>;
+  AM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(args.tiles_m * args.tiles_n * CG), 1, 1);
+  cfg.blockDim = dim3(Cfg::NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tms[0], tms[1], tms[2], tms[3], args));
+  g_launch_count++;
+  return AM_OK;
+}
+
+// A packed operand: two K-major planes (hi, lo) of [Rpad][Kpad] floats, tf32-rounded.
+struct PackedF32 {
+  float* hi; float* lo;
+  int64_t R, K, Rpad, Kpad;
+  bool owned;          // planes were cudaMalloc'd for this object (am_pack_f32) vs. workspace
+};
+
+static int64_t pad_rows(int64_t r) { return round_up(r, 512); }   // either GEMM role (256-row or 512-row tiles)
+static int64_t pad_k(int64_t k) { return round_up(k, 32); }
+
+static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride,
+                     PackedF32* out) {
+  if (out->Rpad / 32 > 65535) { set_last_error("gemm_f32_tc: dimension too large for the pack grid"); return AM_ERR_INVALID; }
+  split_pack_kernel<<<dim3((unsigned)(out->Kpad / 32), (unsigned)(out->Rpad / 32)), 256, 0, st>>>(
+      X, R, K, r_stride, k_stride, out->hi, out->lo, out->Kpad, iabs64(k_stride) <= iabs64(r_stride));
+  g_launch_count++;
+  AM_CUDA_TRY(cudaGetLastError());
+  return AM_OK;
+}
+
+// P rows -> TMEM lanes (C's unit-stride dimension), Q rows -> TMEM columns.
+static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const PackedF32& Q, float alpha,
+                      float beta, float* C, int64_t strideP, int64_t strideQ) {
+  if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
+  static int bk_env = -1;
+  if (bk_env < 0) { const char* e = getenv("AM_TC_BK"); bk_env = (e && atoi(e) == 16) ? 16 : 32; }
+  const int bk = bk_env;
+  CUtensorMap tms[4];
+  int rc;
+  if ((rc = make_tmap(&tms[0], P.hi, P.Rpad, P.Kpad, bk)) || (rc = make_tmap(&tms[1], P.lo, P.Rpad, P.Kpad, bk)) ||
+      (rc = make_tmap(&tms[2], Q.hi, Q.Rpad, Q.Kpad, bk)) || (rc = make_tmap(&tms[3], Q.lo, Q.Rpad, Q.Kpad, bk)))
+    return rc;
+  TcArgs args;
+  args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk);
+  args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
+  if (cta_group == 2) {
+    args.tiles_m = (int)ceil_div(P.R, 256); args.tiles_n = (int)ceil_div(Q.R, 512);
+    return bk == 32 ? launch_tc<2, 32>(st, tms, args) : launch_tc<2, 16>(st, tms, args);
+  }
+  args.tiles_m = (int)ceil_div(P.R, 128); args.tiles_n = (int)ceil_div(Q.R, 256);
+  return bk == 32 ? launch_tc<1, 32>(st, tms, args) : launch_tc<1, 16>(st, tms, args);
+}
+
+int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
+                int64_t rsC, int64_t csC) {
+  if (!gemm_f32_tc_available()) { set_last_error("tcgen05 path needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  if (M >= (1ll << 31) - 1024 || N >= (1ll << 31) - 1024 || K >= (1ll << 31) - 64) { set_last_error("gemm_f32_tc: dimension too large"); return AM_ERR_INVALID; }
+  // Operands in (panel-row stride, k stride) form: A panel rows = m, B panel rows = n.
+  PackedF32 pa{nullptr, nullptr, M, K, pad_rows(M), pad_k(K), false};
+  PackedF32 pb{nullptr, nullptr, N, K, pad_rows(N), pad_k(K), false};
+  void *wsA = nullptr, *wsB = nullptr;
+  int rc = workspace(kWsSplitA, (size_t)(2 * pa.Rpad * pa.Kpad) * sizeof(float), &wsA);
+  if (rc) return rc;
+  rc = workspace(kWsSplitB, (size_t)(2 * pb.Rpad * pb.Kpad) * sizeof(float), &wsB);
+  if (rc) return rc;
+  pa.hi = (float*)wsA; pa.lo = pa.hi + pa.Rpad * pa.Kpad;
+  pb.hi = (float*)wsB; pb.lo = pb.hi + pb.Rpad * pb.Kpad;
+  if ((rc = pack_into(st, A, M, K, rsA, csA, &pa)) || (rc = pack_into(st, B, N, K, csB, rsB, &pb))) return rc;
+  // The epilogue's lanes run along the P rows (TMEM lanes): make that C's unit-stride dimension.
+  // Column-major C (rs == 1, the CudaTensor default): P = A.  Row-major C: C^T = B^T A^T, P = B.
+  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, cta_group, pa, pb, alpha, beta, C, rsC, csC);
+  return run_packed(st, cta_group, pb, pa, alpha, beta, C, csC, rsC);
+}
+
+// ---- pre-packed operands (laser's gemm_prepacked.nim:276-293 on the device): pack once, multiply many
+int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, void** handle) {
+  if (!gemm_f32_tc_available()) { set_last_error("tcgen05 path needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  if (R <= 0 || K <= 0 || !X || !handle) { set_last_error("am_pack_f32: bad argument"); return AM_ERR_INVALID; }
+  PackedF32* p = new PackedF32{nullptr, nullptr, R, K, pad_rows(R), pad_k(K), true};
+  cudaError_t e = cudaMalloc((void**)&p->hi, (size_t)(2 * p->Rpad * p->Kpad) * sizeof(float));
+  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(packed operand)"); }
+  p->lo = p->hi + p->Rpad * p->Kpad;
+  int rc = pack_into(st, X, R, K, r_stride, k_stride, p);
+  if (rc) { cudaFree(p->hi); delete p; return rc; }
+  *handle = p;
+  return AM_OK;
+}
+int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride) {
+  PackedF32* p = (PackedF32*)handle;
+  if (!p || !X) { set_last_error("am_repack_f32: bad argument"); return AM_ERR_INVALID; }
+  return pack_into(st, X, p->R, p->K, r_stride, k_stride, p);
+}
+int packed_free_f32(void* handle) {
+  PackedF32* p = (PackedF32*)handle;
+  if (!p) return AM_OK;
+  if (p->owned && p->hi) cudaFree(p->hi);
+  delete p;
+  return AM_OK;
+}
+int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB, float beta, float* C, int64_t rsC,
+                    int64_t csC) {
+  const PackedF32* a = (const PackedF32*)hA; const PackedF32* b = (const PackedF32*)hB;
+  if (!a || !b || !C) { set_last_error("am_gemm_packed_f32: bad argument"); return AM_ERR_INVALID; }
+  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, 2, *a, *b, alpha, beta, C, rsC, csC);
+  return run_packed(st, 2, *b, *a, alpha, beta, C, csC, rsC);
+}
+
+}  // namespace am

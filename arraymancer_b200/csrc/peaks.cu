@@ -1,0 +1,181 @@
+// On-device micro-benchmarks that define the per-dtype roofline denominators (SURVEY §8d:
+// no datasheet number is trusted).  Each one times a register-resident dependent-chain
+// kernel (SIMT pipes) or a back-to-back tcgen05.mma issue loop (tensor pipe) with CUDA events.
+#include "am_common.cuh"
+#include "gemm_dispatch.h"
+#include "ptx_sm100.cuh"
+
+namespace am {
+
+template <class T, int CHAINS>
+__global__ void __launch_bounds__(256) simt_peak_kernel(T* out, int iters, T a0, T b0) {
+  T acc[CHAINS];
+  T a = a0 + (T)threadIdx.x, b = b0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) acc[i] = (T)i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) acc[i] = mac<T>(a, b, acc[i]);
+    a = (T)(a + acc[0]);       // keep the multiplicand live and data dependent (1 extra op / CHAINS macs)
+  }
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) s = (T)(s + acc[i]);
+  if (s == (T)123457) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// mma.sync m8n8k4 f64: 8x8x4 = 256 FMA per warp instruction
+template <int CHAINS>
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double c0[CHAINS], c1[CHAINS];
+  double a = 1.0 + threadIdx.x * 1e-3, b = 0.999;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) { c0[i] = i; c1[i] = -i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) s += c0[i] + c1[i];
+  if (s == 123457.0) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// back-to-back tcgen05.mma kind::tf32 on resident smem operands: pure tensor-pipe rate
+template <int CG>
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int batch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 8;
+  // pseudo-random tf32 operand bits (so the multipliers toggle like in a real GEMM)
+  for (uint32_t i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) {
+    uint32_t x = i * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    const float f = ((int)(x & 0xffff) - 32768) * (1.0f / 32768.0f);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4 * i), "f"(ptx::to_tf32_rna(f)));
+  }
+  const int warp = threadIdx.x >> 5;
+  const bool leader = (CG == 1) || ptx::cluster_ctarank() == 0;
+  if (CG == 2) ptx::cluster_sync();
+  if (warp == 0 && ptx::elect_one()) { ptx::mbar_init(bar, 1); ptx::fence_barrier_init(); }
+  if (warp == 1) ptx::tmem_alloc<CG>(slot, 256);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (UMMA)
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (warp == 0 && leader && ptx::elect_one()) {
+    const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
+    const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; it++) {
+      for (int j = 0; j < batch; j++) {
+        const uint32_t koff = (uint32_t)(j & 3) * 32;
+        ptx::umma_tf32<CG>(tmem, ptx::umma_desc(dhi, a_s + koff), ptx::umma_desc(dhi, b_s + koff), idesc, (it | j) ? 1u : 0u);
+      }
+      // single-CTA arrive even for CG == 2: only the leader waits
+      asm volatile("tcgen05.commit.cta_group::%1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar), "n"(CG) : "memory");
+      ptx::mbar_wait(bar, ph);
+      ph ^= 1;
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<CG>(tmem, 256);
+}
+
+template <class F>
+static int time_launch(F&& launch, int reps, float* best_ms) {
+  cudaEvent_t e0, e1;
+  AM_CUDA_TRY(cudaEventCreate(&e0));
+  AM_CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; r++) {
+    AM_CUDA_TRY(cudaEventRecord(e0, 0));
+    launch();
+    AM_CUDA_TRY(cudaEventRecord(e1, 0));
+    AM_CUDA_TRY(cudaEventSynchronize(e1));
+    AM_CUDA_TRY(cudaGetLastError());
+    float ms = 0;
+    AM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best) best = ms;   // first rep is warm-up
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *best_ms = best;
+  return AM_OK;
+}
+
+int microbench(int which, double* tops) {
+  if (!tops) { set_last_error("microbench: null output"); return AM_ERR_INVALID; }
+  const int sms = sm_count();
+  void* scratch = nullptr;
+  int rc = workspace(kWsMisc, (size_t)sms * 8 * 256 * 8, &scratch);
+  if (rc) return rc;
+  float ms = 0;
+  const int blocks = sms * 8, threads = 256;
+  double ops = 0;
+  constexpr int CH = 16;
+  switch (which) {
+    case 0: {
+      const int iters = 1 << 15;
+      rc = time_launch([&] { simt_peak_kernel<float, CH><<<blocks, threads>>>((float*)scratch, iters, 1.0001f, 0.9999f); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 1: {
+      const int iters = 1 << 13;
+      rc = time_launch([&] { simt_peak_kernel<double, CH><<<blocks, threads>>>((double*)scratch, iters, 1.0001, 0.9999); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 2: {
+      const int iters = 1 << 15;
+      rc = time_launch([&] { simt_peak_kernel<int32_t, CH><<<blocks, threads>>>((int32_t*)scratch, iters, 3, 5); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 3: {
+      const int iters = 1 << 13;
+      rc = time_launch([&] { simt_peak_kernel<int64_t, CH><<<blocks, threads>>>((int64_t*)scratch, iters, 0x100000003ll, 0x500000007ll); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 4: {
+      const int iters = 1 << 12;
+      rc = time_launch([&] { dmma_peak_kernel<8><<<blocks, threads>>>((double*)scratch, iters); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * 256.0 * 8 * (double)iters * blocks * (threads / 32);
+    } break;
+    case 5:
+    case 6: {
+      if (!gemm_f32_tc_available()) { set_last_error("microbench: tcgen05 needs compute capability 10.x"); return AM_ERR_UNSUPPORTED; }
+      const int cg = which == 5 ? 1 : 2;
+      const int iters = 2000, batch = 16;
+      const int smem = 16384 + 32768 + 64 + 1024;
+      auto k1 = umma_peak_kernel<1>;
+      auto k2 = umma_peak_kernel<2>;
+      AM_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      AM_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int grid = (sms / 2) * 2;
+      rc = time_launch([&] {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cg == 1) cudaLaunchKernelEx(&cfg, k1, iters, batch); else cudaLaunchKernelEx(&cfg, k2, iters, batch);
+        g_launch_count++;
+      }, 3, &ms);
+      ops = 2.0 * (128.0 * cg) * 256.0 * 8.0 * (double)iters * batch * (grid / cg);
+    } break;
+    default:
+      set_last_error("microbench: unknown selector %d", which);
+      return AM_ERR_INVALID;
+  }
+  if (rc) return rc;
+  *tops = ops / (ms * 1e-3) / 1e12;
+  return AM_OK;
+}
+
+}  // namespace am

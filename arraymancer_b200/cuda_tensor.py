@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's CudaTensor operator interface for the dense-contraction
+path.  Same names, argument meaning and error behaviour as
+
+  * tensor/data_structure.nim:44-58          CudaTensor[T] (shape, strides, offset, storage)
+  * tensor/init_cuda.nim:23-59               `.cuda()` (column-major, H2D) / `.cpu()` (D2H)
+  * tensor/operators_blas_l2l3_cuda.nim:43-87  `*`, cudaMM_C_eq_aAB_p_bC
+  * tensor/operators_blas_l2l3.nim:58-100    `gemm(alpha, A, B, beta, C)`
+  * laser/.../gemm.nim:192-201               `gemm_strided` (raw views)
+
+(paths relative to /root/reference/src/arraymancer/).  Nim is not available in this image, so
+this thin Python layer stands where the Nim `{.importc.}` bindings of INTEGRATION.md would;
+torch is used only for device memory and streams.  All arithmetic happens in
+libarraymancer_b200.so — there is no CPU fallback.
+
+Differences from the reference, all supersets: operands may be arbitrary strided views
+(the reference raises ValueError for non-contiguous CUDA operands, operators_blas_l2l3_cuda.nim:49-50,
+marked TODO there) and the element type may be int32/int64 as well as float32/float64
+(reference: SomeFloat only, data_structure.nim:44).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _capi
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.int32: "i32", torch.int64: "i64"}
+_NP2T = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def gemm_strided(alpha, A: torch.Tensor, B: torch.Tensor, beta, C: torch.Tensor) -> torch.Tensor:
+    """C <- alpha*A@B + beta*C on 2-D CUDA views of any stride (laser gemm_strided, gemm.nim:192-201).
+
+    A, B, C are torch CUDA tensors used purely as (device pointer, strides) carriers — exactly
+    what the Nim side passes as (get_offset_ptr, strides[0], strides[1])."""
+    if A.dim() != 2 or B.dim() != 2 or C.dim() != 2:
+        raise ValueError("gemm_strided: operands must be rank-2")
+    if A.dtype not in _SUFFIX or B.dtype != A.dtype or C.dtype != A.dtype:
+        raise TypeError("gemm_strided: operands must share one of float32/float64/int32/int64")
+    if not (A.is_cuda and B.is_cuda and C.is_cuda):
+        raise ValueError("gemm_strided: operands must live on the GPU (no CPU fallback)")
+    M, K = A.shape
+    K2, N = B.shape
+    if K != K2 or tuple(C.shape) != (M, N):
+        # check_matmat (tensor/private/p_checks.nim:159-167) raises IndexDefect
+        raise IndexError(f"gemm_strided: shape mismatch {tuple(A.shape)} * {tuple(B.shape)} -> {tuple(C.shape)}")
+    suf = _SUFFIX[A.dtype]
+    ct = _capi.CTYPE[suf]
+    with torch.cuda.device(C.device):
+        _capi.check(getattr(_capi.lib(), f"am_gemm_strided_{suf}")(
+            _stream_ptr(C), M, N, K, ct(alpha), A.data_ptr(), A.stride(0), A.stride(1),
+            B.data_ptr(), B.stride(0), B.stride(1), ct(beta), C.data_ptr(), C.stride(0), C.stride(1)))
+    return C
+
+
+def cublas_gemm(transa: int, transb: int, m: int, n: int, k: int, alpha, A: torch.Tensor, lda: int,
+                B: torch.Tensor, ldb: int, beta, C: torch.Tensor, ldc: int) -> None:
+    """Column-major cuBLAS-shaped entry (tensor/backend/cublas.nim:142-170); A, B, C are flat
+    device buffers."""
+    suf = _SUFFIX[A.dtype]
+    if suf not in ("f32", "f64"):
+        raise TypeError("cublas_gemm: float32/float64 only (cublas.nim:142 `T: SomeFloat`)")
+    ct = _capi.CTYPE[suf]
+    with torch.cuda.device(C.device):
+        _capi.check(getattr(_capi.lib(), f"am_cublas_gemm_{suf}")(
+            _stream_ptr(C), transa, transb, m, n, k, ct(alpha), A.data_ptr(), lda, B.data_ptr(), ldb,
+            ct(beta), C.data_ptr(), ldc))
+
+
+class CudaTensor:
+    """Mirror of CudaTensor[T] (tensor/data_structure.nim:44-58): shape, strides (in elements),
+    offset, reference-counted device storage.  Default layout is COLUMN-major like the
+    reference (tensor/private/p_init_cuda.nim:29-46)."""
+
+    __slots__ = ("storage", "shape", "strides", "offset")
+
+    def __init__(self, storage: torch.Tensor, shape, strides, offset: int = 0):
+        self.storage = storage            # flat 1-D torch CUDA tensor (owns the cudaMalloc'd block)
+        self.shape = tuple(int(s) for s in shape)
+        self.strides = tuple(int(s) for s in strides)
+        self.offset = int(offset)
+
+    # ---- construction / transfer (init_cuda.nim:23-59)
+    @staticmethod
+    def new(shape, dtype=torch.float32, device="cuda", layout="colMajor") -> "CudaTensor":
+        """newCudaTensor: uninitialised device tensor (p_init_cuda.nim:19-46)."""
+        shape = tuple(int(s) for s in shape)
+        n = int(np.prod(shape)) if shape else 1
+        storage = torch.empty(n, dtype=dtype, device=device)
+        return CudaTensor(storage, shape, _strides_for(shape, layout), 0)
+
+    @property
+    def dtype(self):
+        return self.storage.dtype
+
+    @property
+    def rank(self) -> int:
+        return len(self.shape)
+
+    def view(self) -> torch.Tensor:
+        """The strided torch view (pointer + strides carrier)."""
+        return torch.as_strided(self.storage, self.shape, self.strides, self.offset)
+
+    def cpu(self) -> np.ndarray:
+        """Blocking D2H copy of the whole storage, keeping the strides (init_cuda.nim:43-59)."""
+        host = self.storage.cpu().numpy()
+        it = host.dtype.itemsize
+        return np.lib.stride_tricks.as_strided(host[self.offset:], self.shape, tuple(s * it for s in self.strides))
+
+    # ---- views (tensor/shapeshifting_cuda.nim: transpose is a stride swap, no copy)
+    def transpose(self) -> "CudaTensor":
+        return CudaTensor(self.storage, self.shape[::-1], self.strides[::-1], self.offset)
+
+    def __getitem__(self, idx) -> "CudaTensor":
+        """Basic slicing with steps (negative allowed): offset += a*stride, stride *= step
+        (tensor/private/p_accessors_macros_read.nim:54-58)."""
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        shape, strides, off = [], [], self.offset
+        for d, s in enumerate(idx):
+            if not isinstance(s, slice):
+                raise TypeError("CudaTensor slicing takes slices only")
+            start, stop, step = s.indices(self.shape[d])
+            n = len(range(start, stop, step))
+            off += start * self.strides[d]
+            shape.append(n)
+            strides.append(self.strides[d] * step)
+        for d in range(len(idx), self.rank):
+            shape.append(self.shape[d])
+            strides.append(self.strides[d])
+        return CudaTensor(self.storage, shape, strides, off)
+
+    # ---- `*` (operators_blas_l2l3_cuda.nim:74-87)
+    def __mul__(self, other: "CudaTensor") -> "CudaTensor":
+        return matmul(self, other)
+
+    __matmul__ = __mul__
+
+
+def _strides_for(shape, layout):
+    if layout == "colMajor":
+        st, acc = [], 1
+        for s in shape:
+            st.append(acc)
+            acc *= s
+        return tuple(st)
+    st, acc = [], 1
+    for s in reversed(shape):
+        st.append(acc)
+        acc *= s
+    return tuple(reversed(st))
+
+
+def cuda(t, device="cuda") -> CudaTensor:
+    """`t.cuda()`: asContiguous(colMajor, force=true) then H2D (init_cuda.nim:23-41)."""
+    arr = np.asarray(t)
+    if arr.dtype not in _NP2T:
+        raise TypeError(f"unsupported element type {arr.dtype}")
+    flat = np.ascontiguousarray(arr.T).reshape(-1)       # column-major element order
+    storage = torch.from_numpy(flat).to(device, non_blocking=False)
+    return CudaTensor(storage, arr.shape, _strides_for(arr.shape, "colMajor"), 0)
+
+
+def gemm(alpha, A: CudaTensor, B: CudaTensor, beta, C: CudaTensor) -> None:
+    """C = alpha*A*B + beta*C (tensor/operators_blas_l2l3.nim:58-81; cudaMM_C_eq_aAB_p_bC)."""
+    if A.rank != 2 or B.rank != 2 or C.rank != 2:
+        raise ValueError("gemm: inputs must be matrices")
+    gemm_strided(alpha, A.view(), B.view(), beta, C.view())
+
+
+def matmul(a: CudaTensor, b: CudaTensor) -> CudaTensor:
+    """`a * b` for CudaTensor (operators_blas_l2l3_cuda.nim:74-87): rank-2 x rank-2; result is
+    a fresh column-major tensor, alpha = 1, beta = 0 (never reads the uninitialised C)."""
+    if a.rank == 2 and b.rank == 2:
+        if a.shape[1] != b.shape[0]:
+            raise IndexError(f"matmul: inner dimensions differ: {a.shape} * {b.shape}")   # check_matmat
+        out = CudaTensor.new((a.shape[0], b.shape[1]), a.dtype, a.storage.device)
+        gemm(1, a, b, 0, out)
+        return out
+    if a.rank == 2 and b.rank == 1:
+        if a.shape[1] != b.shape[0]:
+            raise IndexError(f"matmul: inner dimensions differ: {a.shape} * {b.shape}")   # check_matvec
+        # matrix-vector: a GEMM with N = 1 (the reference calls cublas gemv; GEMV is outside the
+        # accelerated path, SURVEY §2.1 — served by the same strided kernel)
+        bv = CudaTensor(b.storage, (b.shape[0], 1), (b.strides[0], 1), b.offset)
+        out = CudaTensor.new((a.shape[0],), a.dtype, a.storage.device)
+        ov = CudaTensor(out.storage, (a.shape[0], 1), (1, a.shape[0]), 0)
+        gemm(1, a, bv, 0, ov)
+        return out
+    raise ValueError("Matrix-Matrix or Matrix-Vector multiplication valid only if first Tensor is a Matrix "
+                     "and second is a Matrix or Vector")

@@ -1,0 +1,175 @@
+/* am_b200.h — C ABI of libarraymancer_b200.so: the B200 (sm_100a) drop-in for Arraymancer's
+ * dense-contraction hot path.  Plain pointers and sizes only; every entry point returns an
+ * int status (0 = AM_OK) so the Nim side can wrap it in `check` exactly like it wraps cuBLAS
+ * (reference: src/arraymancer/tensor/backend/cublas.nim:155-170).  No exceptions or aborts
+ * cross this boundary; am_last_error() returns the message of the last failure on the
+ * calling thread.  All device entry points are asynchronous on the given stream and never
+ * free or retain user pointers.  All paths are relative to /root/reference/src/arraymancer/.
+ *
+ * The reference-side bindings (Nim {.importc, cdecl, dynlib.}) are shown in INTEGRATION.md.
+ */
+#ifndef AM_B200_H
+#define AM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AM_API
+#else
+#define AM_API __attribute__((visibility("default")))
+#endif
+
+typedef void* am_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
+
+enum {
+  AM_OK = 0,
+  AM_ERR_INVALID = 1,     /* bad argument (negative dim, null pointer with non-empty shape, ...) */
+  AM_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed; see am_last_error() */
+  AM_ERR_UNSUPPORTED = 3, /* not built for this device (needs compute capability 10.x) */
+  AM_ERR_NONCONTIGUOUS = 4 /* cuBLAS-shaped entry given a layout it cannot express */
+};
+
+/* ---- introspection ------------------------------------------------------------------- */
+AM_API const char* am_version(void);
+AM_API const char* am_last_error(void);
+AM_API int am_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Frees the per-device workspace caches (split/packed operand panels, conv tables).
+ * Reference scratch is per call (laser/.../gemm_tiling.nim:266-270,326); here it is cached. */
+AM_API int am_shutdown(void);
+
+/* ---- GEMM: mirror of laser gemm_strided ------------------------------------------------
+ * Replaces: laser/primitives/matrix_multiplication/gemm.nim:192-201 (`gemm_strided[T]`, raw
+ * `ptr T` + (rowStride, colStride) in ELEMENTS, any sign / zero) and its unsigned/`int`
+ * overload :275-307 (callers bit-cast uint32/uint64/int to i32/i64, as the reference does).
+ * C <- alpha*A*B + beta*C with A[M,K], B[K,N], C[M,N]; element (r,c) of X at X[r*rs + c*cs].
+ * beta == 0 never reads C (uninitialised / NaN safe, gemm_ukernel_generic.nim:53-60,103-111).
+ * K == 0 leaves C untouched even if beta != 1, like the reference (gemm.nim:203 TODO).
+ * Integers wrap mod 2^n.  Pointers are DEVICE pointers; `stream` is added first.
+ * Callers today: tensor/private/p_operator_blas_l2l3.nim:131 (ints), and after integration
+ * tensor/operators_blas_l2l3.nim:58-71 (floats), nn_primitives/fallback/conv.nim:103,136,140. */
+AM_API int am_gemm_strided_f32(am_stream_t stream, int64_t M, int64_t N, int64_t K, float alpha,
+                               const float* A, int64_t rowStrideA, int64_t colStrideA,
+                               const float* B, int64_t rowStrideB, int64_t colStrideB, float beta,
+                               float* C, int64_t rowStrideC, int64_t colStrideC);
+AM_API int am_gemm_strided_f64(am_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha,
+                               const double* A, int64_t rowStrideA, int64_t colStrideA,
+                               const double* B, int64_t rowStrideB, int64_t colStrideB, double beta,
+                               double* C, int64_t rowStrideC, int64_t colStrideC);
+AM_API int am_gemm_strided_i32(am_stream_t stream, int64_t M, int64_t N, int64_t K, int32_t alpha,
+                               const int32_t* A, int64_t rowStrideA, int64_t colStrideA,
+                               const int32_t* B, int64_t rowStrideB, int64_t colStrideB, int32_t beta,
+                               int32_t* C, int64_t rowStrideC, int64_t colStrideC);
+AM_API int am_gemm_strided_i64(am_stream_t stream, int64_t M, int64_t N, int64_t K, int64_t alpha,
+                               const int64_t* A, int64_t rowStrideA, int64_t colStrideA,
+                               const int64_t* B, int64_t rowStrideB, int64_t colStrideB, int64_t beta,
+                               int64_t* C, int64_t rowStrideC, int64_t colStrideC);
+
+/* Float32 path selector for am_gemm_strided_f32 (process-wide, default AM_F32_AUTO):
+ * AUTO   = tcgen05 3xTF32 (split/packed panels -> TMA -> UMMA, fp32 accumulate in TMEM) for
+ *          shapes that fill tensor tiles, exact-FFMA SIMT kernel for small / skinny shapes;
+ * SIMT   = always the FFMA kernel;  TC = always tcgen05 3xTF32 (any shape, padded);
+ * TC_1CTA = tcgen05 with cta_group::1 tiles (bring-up / comparison). */
+enum { AM_F32_AUTO = 0, AM_F32_SIMT = 1, AM_F32_TC = 2, AM_F32_TC_1CTA = 3 };
+AM_API int am_set_f32_path(int path);
+AM_API int am_get_f32_path(void);
+
+/* ---- pre-packed float32 operands ---------------------------------------------------------
+ * Device-side counterpart of laser's pre-packed GEMM API
+ * (laser/primitives/matrix_multiplication/gemm_prepacked.nim:276-293 `gemm_packed`, with
+ * `gemm_prepackA/B` :178-270): split an operand once into its two K-major tf32 planes and
+ * reuse it over many products (e.g. B across the row chunks of a sharded GEMM, or a weight
+ * matrix across batches).  am_pack_f32_a packs A[M,K] (rows = m), am_pack_f32_b packs B[K,N]
+ * (rows = n); handles own their device memory until am_packed_free_f32.  am_repack_f32_*
+ * refreshes a handle in place from new data of the same shape.
+ * am_gemm_packed_f32: C[M,N] <- alpha*A*B + beta*C on the tcgen05 3xTF32 path. */
+typedef struct am_packed_f32 am_packed_f32;
+AM_API int am_pack_f32_a(am_stream_t stream, int64_t M, int64_t K, const float* A, int64_t rowStrideA,
+                         int64_t colStrideA, am_packed_f32** out);
+AM_API int am_pack_f32_b(am_stream_t stream, int64_t K, int64_t N, const float* B, int64_t rowStrideB,
+                         int64_t colStrideB, am_packed_f32** out);
+AM_API int am_repack_f32_a(am_stream_t stream, am_packed_f32* h, const float* A, int64_t rowStrideA,
+                           int64_t colStrideA);
+AM_API int am_repack_f32_b(am_stream_t stream, am_packed_f32* h, const float* B, int64_t rowStrideB,
+                           int64_t colStrideB);
+AM_API int am_gemm_packed_f32(am_stream_t stream, float alpha, const am_packed_f32* A,
+                              const am_packed_f32* B, float beta, float* C, int64_t rowStrideC,
+                              int64_t colStrideC);
+AM_API int am_packed_free_f32(am_packed_f32* h);
+
+/* ---- cuBLAS-shaped adapter -------------------------------------------------------------
+ * Replaces: tensor/backend/cublas.nim:142-170 `cublas_gemm[T]` (column-major, op N/T), whose
+ * only caller is tensor/operators_blas_l2l3_cuda.nim:68-72 (`cudaMM_C_eq_aAB_p_bC`).
+ * transa/transb: 0 = CUBLAS_OP_N, 1 = CUBLAS_OP_T.  Thin adapter over am_gemm_strided_*:
+ * op N -> (rs=1, cs=ld); op T -> (rs=ld, cs=1); C is always (1, ldc). */
+AM_API int am_cublas_gemm_f32(am_stream_t stream, int transa, int transb, int64_t m, int64_t n,
+                              int64_t k, float alpha, const float* A, int64_t lda, const float* B,
+                              int64_t ldb, float beta, float* C, int64_t ldc);
+AM_API int am_cublas_gemm_f64(am_stream_t stream, int transa, int transb, int64_t m, int64_t n,
+                              int64_t k, double alpha, const double* A, int64_t lda,
+                              const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+
+/* ---- conv2d: fused implicit-GEMM (the im2col buffer is never materialised) ---------------
+ * Replaces: nn_primitives/fallback/conv.nim:81-106 `im2colgemm_conv2d` and :108-140
+ * `im2colgemm_conv2d_gradient` (+ nnp_convolution.nim:91-94 grad_bias), and on the GPU
+ * boundary nn_primitives/nnp_conv2d_cudnn.nim:20-72 `conv2d` / :74-204 `conv2d_backward`.
+ * Layout: input [N,C,H,W], kernel [Cout,C,kH,kW], output / grad_output [N,Cout,Ho,Wo], all
+ * C-contiguous DEVICE buffers pre-allocated by the caller; bias [Cout] or NULL (rank-0 bias).
+ * Ho = (H + 2*padH - (dH*(kH-1)+1)) / sH + 1 (conv.nim:90-91; dilation as in the cuDNN
+ * signature).  Cross-correlation (no kernel flip). */
+typedef struct am_conv2d_desc {
+  int64_t N, C, H, W;
+  int64_t Cout, kH, kW;
+  int64_t padH, padW, strideH, strideW, dilH, dilW;
+} am_conv2d_desc;
+
+AM_API int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo);
+
+#define AM_DECL_CONV(SUF, T)                                                                     \
+  AM_API int am_conv2d_forward_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input, \
+                                     const T* kernel, const T* bias, T* output);                 \
+  /* grad_input / grad_kernel / grad_bias may each be NULL to skip that gradient */             \
+  AM_API int am_conv2d_backward_##SUF(am_stream_t stream, const am_conv2d_desc* d,               \
+                                      const T* input, const T* kernel, const T* grad_output,     \
+                                      T* grad_input, T* grad_kernel, T* grad_bias);
+AM_DECL_CONV(f32, float)
+AM_DECL_CONV(f64, double)
+AM_DECL_CONV(i32, int32_t)
+AM_DECL_CONV(i64, int64_t)
+#undef AM_DECL_CONV
+
+/* ---- host-buffer entry points (the reference-facing "plugin" call with HOST memory) ------
+ * What `a.cuda * b.cuda` followed by `.cpu` does in the reference
+ * (tensor/init_cuda.nim:23-59 + operators_blas_l2l3_cuda.nim:74-87): device buffers are
+ * allocated, operands copied H2D on the call's stream, the GEMM enqueued, the result copied
+ * D2H; returns after the result is in `C` (synchronises the stream).  Strides in elements,
+ * any layout the device entry accepts.  Used by bench.py's `e2e` measurement. */
+AM_API int am_host_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                                    int64_t rsA, int64_t csA, const float* B, int64_t rsB,
+                                    int64_t csB, float beta, float* C, int64_t rsC, int64_t csC);
+AM_API int am_host_gemm_strided_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                                    int64_t rsA, int64_t csA, const double* B, int64_t rsB,
+                                    int64_t csB, double beta, double* C, int64_t rsC, int64_t csC);
+AM_API int am_host_gemm_strided_i32(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t* A,
+                                    int64_t rsA, int64_t csA, const int32_t* B, int64_t rsB,
+                                    int64_t csB, int32_t beta, int32_t* C, int64_t rsC, int64_t csC);
+AM_API int am_host_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t* A,
+                                    int64_t rsA, int64_t csA, const int64_t* B, int64_t rsB,
+                                    int64_t csB, int64_t beta, int64_t* C, int64_t rsC, int64_t csC);
+
+/* ---- measurement helpers (bench.py / profiles) -------------------------------------------
+ * Number of kernels this library has launched on the calling process since load. */
+AM_API int64_t am_kernel_launch_count(void);
+/* On-device micro-benchmarks that define the per-dtype roofline denominators:
+ * which: 0 = FFMA f32, 1 = DFMA f64, 2 = IMAD i32, 3 = i64 multiply-add sequence,
+ *        4 = DMMA m8n8k4 f64 (mma.sync), 5 = tcgen05 kind::tf32 cta_group::1 128x256x8,
+ *        6 = tcgen05 kind::tf32 cta_group::2 256x256x8.
+ * Writes achieved 1e12 op/s (2 ops per multiply-add) to *tops. */
+AM_API int am_microbench(int which, double* tops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AM_B200_H */

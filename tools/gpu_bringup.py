@@ -1,0 +1,230 @@
+"""GPU bring-up / measurement driver: runs each experiment in its own subprocess with a timeout so a
+hung kernel cannot take the whole gpurun call down.  Writes JSON lines to gpurun_out/bringup.jsonl.
+
+  python tools/gpu_bringup.py            # everything
+  python tools/gpu_bringup.py one NAME   # one experiment in-process (used by the parent)
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _time_gpu(fn, warm=2, reps=5):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def exp_peaks():
+    from arraymancer_b200 import _capi
+    names = ["ffma_f32", "dfma_f64", "imad_i32", "i64_mac", "dmma_f64", "umma_tf32_1cta", "umma_tf32_2cta"]
+    res = {}
+    for i, n in enumerate(names):
+        try:
+            res[n] = _capi.microbench(i)
+        except Exception as e:  # noqa
+            res[n] = f"ERR {e}"
+    return res
+
+
+def _rand(shape, dt, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    if dt in ("f32", "f64"):
+        return (rng.random(shape) * 2 - 1).astype({"f32": np.float32, "f64": np.float64}[dt])
+    if dt == "i32":
+        return rng.integers(-2**31, 2**31 - 1, size=shape, dtype=np.int64).astype(np.int32)
+    return rng.integers(-2**63, 2**63 - 1, size=shape, dtype=np.int64)
+
+
+def _parity(dt, M, N, K, path=None, alpha=1, beta=0, layout="rr"):
+    import numpy as np
+    import torch
+    import arraymancer_b200 as am
+    from oracle import laser_oracle as orc
+    if path is not None:
+        am.set_f32_path(path)
+    a, b = _rand((M, K), dt, 1), _rand((K, N), dt, 2)
+    c0 = _rand((M, N), dt, 3)
+    A = torch.from_numpy(a).cuda()
+    B = torch.from_numpy(b).cuda()
+    if layout[0] == "c":
+        A = A.t().contiguous().t()
+    if layout[1] == "c":
+        B = B.t().contiguous().t()
+    C = torch.from_numpy(c0).cuda()
+    if len(layout) > 2 and layout[2] == "c":
+        C = C.t().contiguous().t()
+    am.gemm_strided(alpha, A, B, beta, C)
+    torch.cuda.synchronize()
+    got = C.cpu().numpy()
+    want = c0.copy()
+    orc.gemm_strided(alpha, a, b, beta, want)
+    if dt in ("i32", "i64"):
+        return {"exact": bool(np.array_equal(got, want)), "mismatch": int((got != want).sum())}
+    rel = float(np.linalg.norm(got.astype(np.float64) - want.astype(np.float64)) / np.linalg.norm(want.astype(np.float64)))
+    return {"rel_fro": rel, "finite": bool(np.isfinite(got).all())}
+
+
+def exp_simt_parity():
+    res = {}
+    for dt in ("i64", "i32", "f64", "f32"):
+        for (M, N, K) in [(5, 7, 3), (64, 64, 64), (129, 65, 300), (257, 513, 100), (1500, 1500, 1500)]:
+            for lay in ("rr", "cc", "rrc"):
+                res[f"{dt}_{M}x{N}x{K}_{lay}"] = _parity(dt, M, N, K, path=1, alpha=1, beta=0, layout=lay)
+        res[f"{dt}_alpha_beta"] = _parity(dt, 100, 90, 80, path=1, alpha=-3, beta=2)
+    return res
+
+
+def _tc_parity(path, bk):
+    os.environ["AM_TC_BK"] = str(bk)
+    res = {}
+    for (M, N, K) in [(128, 256, 32), (256, 512, 64), (512, 512, 256), (300, 700, 100), (1024, 2048, 1024)]:
+        for lay in ("rr", "rrc", "cc"):
+            res[f"{M}x{N}x{K}_{lay}"] = _parity("f32", M, N, K, path=path, layout=lay)
+    res["alpha_beta"] = _parity("f32", 512, 512, 512, path=path, alpha=-3, beta=2)
+    return res
+
+
+def exp_tc1_bk32(): return _tc_parity(3, 32)
+def exp_tc1_bk16(): return _tc_parity(3, 16)
+def exp_tc2_bk32(): return _tc_parity(2, 32)
+def exp_tc2_bk16(): return _tc_parity(2, 16)
+
+
+def _gemm_speed(dt, n, path=None, reps=5):
+    import torch
+    import arraymancer_b200 as am
+    if path is not None:
+        am.set_f32_path(path)
+    tdt = {"f32": torch.float32, "f64": torch.float64, "i32": torch.int32, "i64": torch.int64}[dt]
+    if dt in ("f32", "f64"):
+        A = torch.rand(n, n, device="cuda", dtype=tdt) * 2 - 1
+        B = torch.rand(n, n, device="cuda", dtype=tdt) * 2 - 1
+    else:
+        A = torch.randint(0, 100, (n, n), device="cuda", dtype=tdt)
+        B = torch.randint(0, 100, (n, n), device="cuda", dtype=tdt)
+    C = torch.empty(n, n, device="cuda", dtype=tdt)
+    med, best = _time_gpu(lambda: am.gemm_strided(1, A, B, 0, C), reps=reps)
+    return {"ms_med": med, "ms_best": best, "tops_med": 2 * n**3 / med / 1e9, "tops_best": 2 * n**3 / best / 1e9}
+
+
+def exp_simt_speed():
+    res = {}
+    for dt, n in [("i64", 1500), ("i64", 4096), ("i32", 1500), ("i32", 4096), ("f64", 1500), ("f64", 4096),
+                  ("f64", 8192), ("f32", 4096)]:
+        res[f"{dt}_{n}"] = _gemm_speed(dt, n, path=1, reps=3)
+    return res
+
+
+def _tc_speed(path, bk):
+    os.environ["AM_TC_BK"] = str(bk)
+    res = {}
+    for n in (4096, 8192, 16384):
+        res[f"f32_{n}"] = _gemm_speed("f32", n, path=path, reps=3)
+    return res
+
+
+def exp_tc1_speed_bk32(): return _tc_speed(3, 32)
+def exp_tc2_speed_bk32(): return _tc_speed(2, 32)
+def exp_tc2_speed_bk16(): return _tc_speed(2, 16)
+def exp_tc1_speed_bk16(): return _tc_speed(3, 16)
+
+
+def exp_conv_parity():
+    import numpy as np
+    import torch
+    import arraymancer_b200 as am
+    from oracle import laser_oracle as orc
+    res = {}
+    rng = np.random.default_rng(0)
+    cases = [((2, 3, 4, 5), (2, 3, 3, 3), (1, 1), (1, 1), (1, 1)), ((3, 1, 28, 28), (20, 1, 5, 5), (0, 0), (1, 1), (1, 1)),
+             ((2, 20, 12, 12), (50, 20, 5, 5), (0, 0), (1, 1), (1, 1)), ((2, 4, 9, 8), (5, 4, 3, 2), (1, 2), (2, 1), (1, 1)),
+             ((2, 3, 11, 10), (70, 3, 3, 3), (2, 2), (1, 1), (2, 2)), ((1, 130, 6, 6), (6, 130, 3, 3), (1, 0), (2, 2), (2, 1))]
+    for dt in ("f32", "f64", "i32", "i64"):
+        for ci, (xs, ks, pad, st, dil) in enumerate(cases):
+            if dt in ("f32", "f64"):
+                npdt = np.float32 if dt == "f32" else np.float64
+                x = rng.random(xs).astype(npdt); k = (rng.random(ks) - 0.5).astype(npdt); b = rng.random((ks[0], 1, 1)).astype(npdt)
+            else:
+                npdt = np.int32 if dt == "i32" else np.int64
+                x = rng.integers(-9, 9, xs).astype(npdt); k = rng.integers(-9, 9, ks).astype(npdt); b = rng.integers(-9, 9, (ks[0], 1, 1)).astype(npdt)
+            want = orc.conv2d(x, k, b, pad, st, dil)
+            X, K_, B_ = (torch.from_numpy(v).cuda() for v in (x, k, b))
+            got = am.conv2d(X, K_, B_, pad, st, dil).cpu().numpy()
+            go = (rng.random(want.shape) * 2 - 1).astype(npdt) if dt in ("f32", "f64") else rng.integers(-5, 5, want.shape).astype(npdt)
+            wgi, wgw, wgb = orc.conv2d_backward(x, k, go, True, pad, st, dil)
+            gi, gw, gb = am.conv2d_backward(X, K_, B_, pad, st, dil, torch.from_numpy(go).cuda())
+            gi, gw, gb = gi.cpu().numpy(), gw.cpu().numpy(), gb.cpu().numpy()
+            if dt in ("i32", "i64"):
+                res[f"{dt}_{ci}"] = {"fwd": bool(np.array_equal(got, want)), "gin": bool(np.array_equal(gi, wgi)),
+                                     "gw": bool(np.array_equal(gw, wgw)), "gb": bool(np.array_equal(gb, wgb))}
+            else:
+                f = lambda a_, b_: float(np.linalg.norm(a_.astype(np.float64) - b_) / max(np.linalg.norm(b_.astype(np.float64)), 1e-30))
+                res[f"{dt}_{ci}"] = {"fwd": f(got, want), "gin": f(gi, wgi), "gw": f(gw, wgw), "gb": f(gb, wgb)}
+    return res
+
+
+def exp_conv_speed():
+    import torch
+    import arraymancer_b200 as am
+    res = {}
+    for name, xs, ks in [("cv1", (4096, 1, 28, 28), (20, 1, 5, 5)), ("cv2", (4096, 20, 12, 12), (50, 20, 5, 5))]:
+        X = torch.rand(xs, device="cuda"); K_ = torch.randn(ks, device="cuda") * 0.1; B_ = torch.zeros(ks[0], 1, 1, device="cuda")
+        out = am.conv2d(X, K_, B_)
+        go = torch.ones_like(out)
+        med, best = _time_gpu(lambda: am.conv2d(X, K_, B_), reps=5)
+        bmed, bbest = _time_gpu(lambda: am.conv2d_backward(X, K_, B_, (0, 0), (1, 1), (1, 1), go), reps=5)
+        flops = 2 * out.numel() * ks[1] * ks[2] * ks[3]
+        res[name] = {"fwd_ms": med, "fwd_gflops": flops / med / 1e6, "bwd_ms": bmed, "bwd_gflops": 2 * flops / bmed / 1e6}
+    return res
+
+
+EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_bk32", "tc2_bk32", "tc1_bk16", "tc2_bk16", "simt_speed",
+               "tc1_speed_bk32", "tc2_speed_bk32", "tc2_speed_bk16", "tc1_speed_bk16", "conv_speed"]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) >= 3 and sys.argv[1] == "one":
+        name = sys.argv[2]
+        r = globals()[f"exp_{name}"]()
+        print("RESULT " + json.dumps({"exp": name, "result": r}))
+        return
+    names = sys.argv[1:] or EXPERIMENTS
+    with open(os.path.join(OUT, "bringup.jsonl"), "a") as f:
+        for name in names:
+            t0 = time.time()
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "one", name], capture_output=True,
+                                   text=True, timeout=420)
+                line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+                rec = json.loads(line[-1][7:]) if line else {"exp": name, "error": (p.stdout[-1500:] + p.stderr[-3000:])}
+                rec["rc"] = p.returncode
+            except subprocess.TimeoutExpired:
+                rec = {"exp": name, "error": "TIMEOUT"}
+            rec["secs"] = round(time.time() - t0, 1)
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            print(json.dumps(rec)[:3000], flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,9 +5,9 @@ libarraymancer_b200.so (C ABI: include/am_b200.h); this package is the thin host
 the reference's operator interface.  There is no CPU fallback."""
 from . import _capi
 from ._capi import AmError, F32_AUTO, F32_SIMT, F32_TC, F32_TC_1CTA, set_f32_path, version
-from .cuda_tensor import CudaTensor, cuda, cublas_gemm, gemm, gemm_strided, matmul
+from .cuda_tensor import CudaTensor, PackedF32, cuda, cublas_gemm, gemm, gemm_packed, gemm_strided, matmul
 from .nn_primitives import conv2d, conv2d_backward, conv_out_dims
 
-__all__ = ["AmError", "CudaTensor", "cuda", "cublas_gemm", "gemm", "gemm_strided", "matmul", "conv2d",
+__all__ = ["AmError", "CudaTensor", "cuda", "cublas_gemm", "gemm", "gemm_strided", "gemm_packed", "PackedF32", "matmul", "conv2d",
            "conv2d_backward", "conv_out_dims", "set_f32_path", "version", "F32_AUTO", "F32_SIMT", "F32_TC",
            "F32_TC_1CTA"]

@@ -19,6 +19,8 @@ marked TODO there) and the element type may be int32/int64 as well as float32/fl
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -42,13 +44,13 @@ def gemm_strided(alpha, A: torch.Tensor, B: torch.Tensor, beta, C: torch.Tensor)
         raise ValueError("gemm_strided: operands must be rank-2")
     if A.dtype not in _SUFFIX or B.dtype != A.dtype or C.dtype != A.dtype:
         raise TypeError("gemm_strided: operands must share one of float32/float64/int32/int64")
-    if not (A.is_cuda and B.is_cuda and C.is_cuda):
-        raise ValueError("gemm_strided: operands must live on the GPU (no CPU fallback)")
     M, K = A.shape
     K2, N = B.shape
     if K != K2 or tuple(C.shape) != (M, N):
         # check_matmat (tensor/private/p_checks.nim:159-167) raises IndexDefect
         raise IndexError(f"gemm_strided: shape mismatch {tuple(A.shape)} * {tuple(B.shape)} -> {tuple(C.shape)}")
+    if not (A.is_cuda and B.is_cuda and C.is_cuda):
+        raise ValueError("gemm_strided: operands must live on the GPU (no CPU fallback)")
     suf = _SUFFIX[A.dtype]
     ct = _capi.CTYPE[suf]
     with torch.cuda.device(C.device):
@@ -194,3 +196,49 @@ def matmul(a: CudaTensor, b: CudaTensor) -> CudaTensor:
         return out
     raise ValueError("Matrix-Matrix or Matrix-Vector multiplication valid only if first Tensor is a Matrix "
                      "and second is a Matrix or Vector")
+
+
+class PackedF32:
+    """Pre-packed float32 operand for the tcgen05 3xTF32 path (am_pack_f32_a / am_pack_f32_b;
+    device counterpart of laser's gemm_prepackA/B, gemm_prepacked.nim:178-270): split once into
+    two K-major tf32 planes, reuse over many products."""
+
+    def __init__(self, t: torch.Tensor, role: str):
+        if t.dim() != 2 or t.dtype != torch.float32 or not t.is_cuda:
+            raise ValueError("PackedF32: rank-2 float32 CUDA tensor expected")
+        if role not in ("a", "b"):
+            raise ValueError("PackedF32: role must be 'a' (A[M,K]) or 'b' (B[K,N])")
+        self.role, self.shape, self.device = role, tuple(t.shape), t.device
+        self._h = ctypes.c_void_p()
+        fn = getattr(_capi.lib(), f"am_pack_f32_{role}")
+        with torch.cuda.device(t.device):
+            _capi.check(fn(_stream_ptr(t), t.shape[0], t.shape[1], t.data_ptr(), t.stride(0), t.stride(1),
+                           ctypes.byref(self._h)))
+
+    def repack(self, t: torch.Tensor) -> None:
+        if tuple(t.shape) != self.shape or t.dtype != torch.float32:
+            raise ValueError("PackedF32.repack: shape / dtype must match the original operand")
+        fn = getattr(_capi.lib(), f"am_repack_f32_{self.role}")
+        with torch.cuda.device(t.device):
+            _capi.check(fn(_stream_ptr(t), self._h, t.data_ptr(), t.stride(0), t.stride(1)))
+
+    def free(self) -> None:
+        if self._h:
+            _capi.lib().am_packed_free_f32(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def gemm_packed(alpha: float, A: PackedF32, B: PackedF32, beta: float, C: torch.Tensor) -> torch.Tensor:
+    """C <- alpha*A*B + beta*C from pre-packed operands (gemm_prepacked.nim:276-293 `gemm_packed`)."""
+    if A.role != "a" or B.role != "b" or A.shape[1] != B.shape[0] or tuple(C.shape) != (A.shape[0], B.shape[1]):
+        raise IndexError("gemm_packed: operand roles / shapes do not match")
+    with torch.cuda.device(C.device):
+        _capi.check(_capi.lib().am_gemm_packed_f32(_stream_ptr(C), alpha, A._h, B._h, beta, C.data_ptr(),
+                                                   C.stride(0), C.stride(1)))
+    return C

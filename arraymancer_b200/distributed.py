@@ -1,0 +1,114 @@
+"""Multi-GPU sharding of the hot path — one process per GPU, torch.distributed for the plumbing.
+
+The reference has no multi-device code at all; parity is defined against the
+single-device result:
+
+  * Large GEMM: rows of A (and of C) are dealt to the ranks in block-cyclic chunks, B is replicated.
+    Rank r owns, for every chunk index j, the rows [(j*g + r)*mc, (j*g + r + 1)*mc).  With that
+    layout the all-gather of chunk j over the ranks fills the CONTIGUOUS row range
+    [j*g*mc, (j+1)*g*mc) of the full row-major C, so every chunk is one in-place
+    `all_gather_into_tensor` — issued on a communication stream while the GEMM of chunk j+1 runs
+    (compute of chunk j+1 overlaps the NVLink transfer of chunk j).  No K split, so integer results
+    stay bit-exact and float results are identical to the 1-GPU result.
+  * Batched conv2d: images are independent — the batch is split over the ranks, weights are
+    replicated; backward all-reduces grad_kernel / grad_bias (sum), grad_input stays sharded.
+
+`local_gemm` / `local_conv*` are injectable so the host-side logic (partitioning + collectives) is
+testable with the gloo backend on CPU (tests/test_distributed_cpu.py plugs the oracle in there);
+on GPUs they default to the CUDA kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def chunk_rows(M: int, world: int, chunks: int) -> int:
+    """Rows per (rank, chunk) block; M must split evenly (pad the operand otherwise)."""
+    if M % (world * chunks) != 0:
+        raise ValueError(f"row-sharded GEMM: M={M} must be a multiple of world*chunks={world * chunks}")
+    return M // (world * chunks)
+
+
+def owned_row_ranges(M: int, world: int, rank: int, chunks: int):
+    """Global row ranges [(start, stop)] owned by `rank`, in local storage order."""
+    mc = chunk_rows(M, world, chunks)
+    return [((j * world + rank) * mc, (j * world + rank + 1) * mc) for j in range(chunks)]
+
+
+def shard_rows(A_full: torch.Tensor, world: int, rank: int, chunks: int) -> torch.Tensor:
+    """Pick this rank's block-cyclic rows out of a full A (test / setup helper)."""
+    return torch.cat([A_full[a:b] for a, b in owned_row_ranges(A_full.shape[0], world, rank, chunks)], dim=0)
+
+
+class RowShardedGemm:
+    """C[M,N] = A[M,K] @ B[K,N] with A's rows dealt over the ranks and the full C gathered on every
+    rank.  `A_local` holds this rank's rows ([chunks*mc, K], chunk-major); `B` is replicated."""
+
+    def __init__(self, M: int, N: int, K: int, dtype, device, chunks: int = 4, group=None, local_gemm=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.M, self.N, self.K, self.chunks = M, N, K, chunks
+        self.mc = chunk_rows(M, self.world, chunks)
+        self.C = torch.empty((M, N), dtype=dtype, device=device)      # full result, row-major
+        self.cuda = torch.device(device).type == "cuda"
+        if local_gemm is None:
+            from .cuda_tensor import gemm_strided
+            local_gemm = lambda A, B, C: gemm_strided(1, A, B, 0, C)  # noqa: E731
+        self.local_gemm = local_gemm
+        self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
+
+    def __call__(self, A_local: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        g, r, mc = self.world, self.rank, self.mc
+        works = []
+        for j in range(self.chunks):
+            lo = (j * g + r) * mc
+            mine = self.C[lo:lo + mc]
+            self.local_gemm(A_local[j * mc:(j + 1) * mc], B, mine)
+            if g == 1:
+                continue
+            span = self.C[j * g * mc:(j + 1) * g * mc]
+            if self.cuda:
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ready)
+                    works.append(dist.all_gather_into_tensor(span, mine, group=self.group, async_op=True))
+            else:
+                parts = [span[i * mc:(i + 1) * mc] for i in range(g)]
+                dist.all_gather(parts, mine.clone(), group=self.group)
+        for w in works:
+            w.wait()
+        if self.cuda and g > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        return self.C
+
+
+def shard_batch(n_images: int, world: int, rank: int):
+    """Contiguous image range of `rank` (the remainder goes to the first ranks)."""
+    base, rem = divmod(n_images, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def conv2d_batch_sharded(x_local, kernel, bias, padding=(0, 0), strides=(1, 1), dilation=(1, 1), local_conv=None):
+    """Forward on this rank's images; the output stays batch-sharded (no collective)."""
+    if local_conv is None:
+        from .nn_primitives import conv2d as local_conv
+    return local_conv(x_local, kernel, bias, padding, strides, dilation)
+
+
+def conv2d_backward_batch_sharded(x_local, kernel, bias, padding, strides, dilation, grad_out_local, group=None,
+                                  local_conv_backward=None):
+    """Backward on this rank's images: grad_input stays sharded, grad_kernel / grad_bias are summed
+    over the ranks (all-reduce; float summation order differs from the serial reference loop, covered
+    by the stated backward tolerance; integers stay exact)."""
+    if local_conv_backward is None:
+        from .nn_primitives import conv2d_backward as local_conv_backward
+    gin, gk, gb = local_conv_backward(x_local, kernel, bias, padding, strides, dilation, grad_out_local)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(gk, op=dist.ReduceOp.SUM, group=group)
+        if gb is not None:
+            dist.all_reduce(gb, op=dist.ReduceOp.SUM, group=group)
+    return gin, gk, gb

@@ -67,48 +67,58 @@ split_pack_kernel(const float* __restrict__ X, int64_t R, int64_t K, int64_t r_s
 }
 
 // ------------------------------------------------------------------ mainloop
-template <int CG, int BK>
+// Why the accumulators live in REGISTERS, not only in TMEM: the tensor core adds each MMA result
+// into its fp32 accumulator with truncation, a bias that grows linearly with the length of the
+// accumulation chain (measured on B200: rel. error ~7e-9 * K for one chain over all of K, i.e.
+// 1e-4 at K = 16384 — not fp32 accuracy; profiles/r01_bringup.md).  So a chain only spans
+// `flush_kb` k-blocks (64-128 k): each chain starts with accumulate = 0 into one of two 256-column
+// TMEM buffers, and the 8 accumulate warps drain the finished buffer with tcgen05.ld and add it
+// into their register tile with round-to-nearest FADDs while the next chain fills the other buffer.
+template <int CG>
 struct TcCfg {
+  static constexpr int BK = 32;                      // floats per k-block = one 128-B swizzle row
   static constexpr int ROWS_A = 128;                 // A rows staged per CTA (= UMMA M per CTA)
-  static constexpr int ROWS_B = 256;                 // B rows staged per CTA
+  static constexpr int ROWS_B = (CG == 2) ? 128 : 256;   // B rows staged per CTA (pair: half of the 256 columns)
   static constexpr int TILE_M = 128 * CG;            // output tile of the CTA (pair)
-  static constexpr int TILE_N = 256 * CG;
-  static constexpr int NHALF = CG;                   // accumulator halves of 256 columns
-  static constexpr int TMEM_COLS = 256 * CG;
-  static constexpr int ROW_BYTES = BK * 4;           // 128 (SW128) or 64 (SW64)
+  static constexpr int TILE_N = 256;
+  static constexpr int TMEM_COLS = 512;              // two ping-pong chain buffers of 256 columns
+  static constexpr int ROW_BYTES = BK * 4;
   static constexpr int SBO = 8 * ROW_BYTES;
-  static constexpr int BOX_BYTES = 128 * ROW_BYTES;  // one TMA box: 128 rows x BK floats
+  static constexpr int BOX_BYTES = 128 * ROW_BYTES;  // one TMA box: 128 rows x 32 floats = 16 KB
   static constexpr int A_BYTES = BOX_BYTES;          // per plane
-  static constexpr int B_BYTES = 2 * BOX_BYTES;      // per plane
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // 2 @ BK=32, 4 @ BK=16
+  static constexpr int B_BYTES = (ROWS_B / 128) * BOX_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // 64 KB (pair) / 96 KB (single)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;              // 3 (pair) / 2 (single)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int NTHREADS = 192;
+  static constexpr int NTHREADS = 384;               // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: accumulate
 };
 
 struct TcArgs {
   int64_t M, N;            // logical output extent (rows = TMEM lanes, cols = TMEM columns)
-  int kblocks;             // Kpad / BK
+  int kblocks;             // Kpad / 32
+  int flush_kb;            // k-blocks per tensor-core accumulation chain
   int tiles_m, tiles_n;
   float* C; int64_t rsC, csC;
   float alpha, beta;
 };
 
-template <int CG, int BK>
-__global__ void __launch_bounds__(192, 1)
+template <int CG>
+__global__ void __launch_bounds__(384, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                    const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                    const TcArgs p) {
-  using Cfg = TcCfg<CG, BK>;
+  using Cfg = TcCfg<CG>;
+  constexpr int BK = Cfg::BK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;      // SW128 needs 1024-B alignment
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   auto stage_base = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
-  // stage layout: [A_hi | A_lo | B_hi (256 rows) | B_lo (256 rows)]
+  // stage layout: [A_hi | A_lo | B_hi | B_lo]
   constexpr uint32_t OFF_AHI = 0, OFF_ALO = Cfg::A_BYTES, OFF_BHI = 2 * Cfg::A_BYTES, OFF_BLO = 2 * Cfg::A_BYTES + Cfg::B_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -116,7 +126,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
 
-  // tile of this CTA (pair): grouped rasterisation, 8 M-tiles per group, for L2 reuse of B panels
+  // tile of this CTA (pair): grouped rasterisation, 8 M-tiles per group, for L2 reuse of the B panels
   const int tile = (int)(blockIdx.x / CG);
   constexpr int GROUP = 8;
   const int group_size = GROUP * p.tiles_n;
@@ -139,7 +149,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       ptx::mbar_init(full_bar(s), CG);      // one arrival per producer CTA (both arrive on the leader's)
       ptx::mbar_init(empty_bar(s), 1);      // one tcgen05.commit (multicast to both CTAs when CG == 2)
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      ptx::mbar_init(tfull_bar(b), 1);          // chain complete (commit, multicast)
+      ptx::mbar_init(tempty_bar(b), 8 * CG);    // buffer drained: one arrival per accumulate warp of every CTA (leader's barrier)
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
@@ -150,104 +163,126 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int nkb = p.kblocks;
+  const int flush = p.flush_kb;
+  const int nchains = (nkb + flush - 1) / flush;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one elected lane, in every CTA) =====================
-    if (ptx::elect_one()) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t sb = stage_base(s);
-        const int kc = kb * BK;
-        if constexpr (CG == 1) {
-          const uint32_t fb = full_bar(s);
-          ptx::mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(sb + OFF_AHI, &tmAhi, fb, kc, row0);
-          ptx::tma_load_2d(sb + OFF_ALO, &tmAlo, fb, kc, row0);
-          ptx::tma_load_2d(sb + OFF_BHI, &tmBhi, fb, kc, col0);
-          ptx::tma_load_2d(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, col0 + 128);
-          ptx::tma_load_2d(sb + OFF_BLO, &tmBlo, fb, kc, col0);
-          ptx::tma_load_2d(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, col0 + 128);
-        } else {
-          // all transaction bytes of both CTAs land on the LEADER's full barrier
-          const uint32_t fb = ptx::mapa(full_bar(s), 0);
-          if (leader) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-          else ptx::mbar_arrive_cluster(fb);
-          // accumulator half h covers output columns col0 + h*256 .. +255; this CTA supplies the
-          // B rows [rank*128, rank*128+128) of each half
-          const int b0 = col0 + (int)cta_rank * 128;
-          ptx::tma_load_2d_pair(sb + OFF_AHI, &tmAhi, fb, kc, row0);
-          ptx::tma_load_2d_pair(sb + OFF_ALO, &tmAlo, fb, kc, row0);
-          ptx::tma_load_2d_pair(sb + OFF_BHI, &tmBhi, fb, kc, b0);
-          ptx::tma_load_2d_pair(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, b0 + 256);
-          ptx::tma_load_2d_pair(sb + OFF_BLO, &tmBlo, fb, kc, b0);
-          ptx::tma_load_2d_pair(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, b0 + 256);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== UMMA issuer (leader CTA only, one elected lane) =====================
-    if (leader && ptx::elect_one()) {
-      const uint64_t dhi = ptx::umma_desc_hi(Cfg::SBO, Cfg::ROW_BYTES);
-      const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-        ptx::mbar_wait(full_bar(s), ph);
-        ptx::tc_fence_after();
-        const uint32_t sb = stage_base(s);
-#pragma unroll
-        for (int k8 = 0; k8 < BK / 8; k8++) {
-          const uint32_t koff = k8 * 32;                         // 8 tf32 = 32 bytes along K inside the swizzle atom
-          const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff);
-          const uint64_t a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
-#pragma unroll
-          for (int h = 0; h < Cfg::NHALF; h++) {
-            // CG == 1: one 256-row B operand.  CG == 2: half h = this CTA's 128-row block h (peer supplies the rest)
-            const uint32_t boff = (CG == 2) ? (uint32_t)h * Cfg::BOX_BYTES : 0u;
-            const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + boff + koff);
-            const uint64_t b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + boff + koff);
-            const uint32_t d = tmem_base + (uint32_t)h * 256u;
-            const uint32_t first = (kb == 0 && k8 == 0) ? 0u : 1u;
-            ptx::umma_tf32<CG>(d, a_lo, b_hi, idesc, first);     // small terms first
-            ptx::umma_tf32<CG>(d, a_hi, b_lo, idesc, 1u);
-            ptx::umma_tf32<CG>(d, a_hi, b_hi, idesc, 1u);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer (one elected lane, in every CTA) =====================
+      if (ptx::elect_one()) {
+        for (int kb = 0; kb < nkb; kb++) {
+          const int s = kb % Cfg::STAGES;
+          const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sb = stage_base(s);
+          const int kc = kb * BK;
+          if constexpr (CG == 1) {
+            const uint32_t fb = full_bar(s);
+            ptx::mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+            ptx::tma_load_2d(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+            ptx::tma_load_2d(sb + OFF_BHI, &tmBhi, fb, kc, col0);
+            ptx::tma_load_2d(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, col0 + 128);
+            ptx::tma_load_2d(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+            ptx::tma_load_2d(sb + OFF_BLO, &tmBlo, fb, kc, col0);
+            ptx::tma_load_2d(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, col0 + 128);
+          } else {
+            // all transaction bytes of both CTAs land on the LEADER's full barrier
+            const uint32_t fb = ptx::mapa(full_bar(s), 0);
+            if (leader) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+            else ptx::mbar_arrive_cluster(fb);
+            const int b0 = col0 + (int)cta_rank * 128;     // this CTA supplies B rows [rank*128, +128) of the 256 columns
+            ptx::tma_load_2d_pair(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+            ptx::tma_load_2d_pair(sb + OFF_BHI, &tmBhi, fb, kc, b0);
+            ptx::tma_load_2d_pair(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+            ptx::tma_load_2d_pair(sb + OFF_BLO, &tmBlo, fb, kc, b0);
           }
         }
-        ptx::umma_commit<CG>(empty_bar(s));                      // frees the stage in both CTAs once the MMAs retire
-        if (kb == nkb - 1) ptx::umma_commit<CG>(tmem_full_bar);  // accumulators complete
+      }
+    } else if (warp == 1) {
+      // ===================== UMMA issuer (leader CTA only, one elected lane) =====================
+      if (leader && ptx::elect_one()) {
+        const uint64_t dhi = ptx::umma_desc_hi(Cfg::SBO, Cfg::ROW_BYTES);
+        const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
+        int kb = 0;
+        for (int c = 0; c < nchains; c++) {
+          const int buf = c & 1;
+          ptx::mbar_wait(tempty_bar(buf), (((uint32_t)c >> 1) & 1u) ^ 1u);    // accumulate warps drained this buffer
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+          const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
+          for (bool first = true; kb < kb_end; kb++) {
+            const int s = kb % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            ptx::mbar_wait(full_bar(s), ph);
+            ptx::tc_fence_after();
+            const uint32_t sb = stage_base(s);
+#pragma unroll
+            for (int k8 = 0; k8 < BK / 8; k8++) {
+              const uint32_t koff = k8 * 32;                       // 8 tf32 = 32 bytes along K inside the swizzle atom
+              const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff);
+              const uint64_t a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
+              const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff);
+              const uint64_t b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
+              ptx::umma_tf32<CG>(d, a_lo, b_hi, idesc, first ? 0u : 1u);   // small terms first
+              ptx::umma_tf32<CG>(d, a_hi, b_lo, idesc, 1u);
+              ptx::umma_tf32<CG>(d, a_hi, b_hi, idesc, 1u);
+              first = false;
+            }
+            ptx::umma_commit<CG>(empty_bar(s));                    // frees the stage in both CTAs once the MMAs retire
+          }
+          ptx::umma_commit<CG>(tfull_bar(buf));                    // chain complete -> accumulate warps
+        }
       }
     }
   } else {
-    // ===================== epilogue warps 2..5: TMEM -> registers -> global =====================
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const int q = warp & 3;                                      // TMEM lane quarter this warp may access
-    const int64_t m = (int64_t)row0 + q * 32 + (int)lane;
-    const bool m_ok = m < p.M;
-    float* crow = p.C + m * p.rsC;
-    const float alpha = p.alpha, beta = p.beta;
-    for (int c = 0; c < Cfg::TMEM_COLS; c += 32) {
-      if ((int64_t)col0 + c >= p.N) break;                       // warp-uniform
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      ptx::tmem_ld_wait();
-      if (m_ok) {
+    // ===================== accumulate / epilogue warps 4..11 =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;              // which 128 of the 256 columns
+    float acc[128];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int64_t n = (int64_t)col0 + c + j;
-          if (n < p.N) {
-            float* pc = crow + n * p.csC;
-            const float cold = (beta != 0.f) ? *pc : 0.f;
-            *pc = epilogue_value<float>(alpha, __uint_as_float(r[j]), beta, cold);
-          }
+    for (int i = 0; i < 128; i++) acc[i] = 0.f;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 128u;
+    const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    for (int c = 0; c < nchains; c++) {
+      const int buf = c & 1;
+      ptx::mbar_wait(tfull_bar(buf), ((uint32_t)c >> 1) & 1u);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tlane + (uint32_t)buf * 256u + (uint32_t)j * 32u, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(r[i]));
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * buf);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+      }
+    }
+    // ---- epilogue: alpha/beta, strided stores (lanes run along C's unit-stride dimension)
+    const int64_t m = (int64_t)row0 + q * 32 + (int)lane;
+    if (m < p.M) {
+      float* crow = p.C + m * p.rsC;
+      const float alpha = p.alpha, beta = p.beta;
+#pragma unroll
+      for (int i = 0; i < 128; i++) {
+        const int64_t n = (int64_t)col0 + half * 128 + i;
+        if (n < p.N) {
+          float* pc = crow + n * p.csC;
+          const float cold = (beta != 0.f) ? *pc : 0.f;
+          *pc = epilogue_value<float>(alpha, acc[i], beta, cold);
         }
       }
     }
   }
 
   // teardown: nobody may leave (or free TMEM) while the pair still has traffic in flight
+  __syncwarp();
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
@@ -291,10 +326,10 @@ static int make_tmap(CUtensorMap* tm, float* base, int64_t rows, int64_t kpad, i
   return AM_OK;
 }
 
-template <int CG, int BK>
+template <int CG>
 static int launch_tc(cudaStream_t st, const CUtensorMap* tms, const TcArgs& args) {
-  using Cfg = TcCfg<CG, BK>;
-  auto kern = gemm_tf32x3_kernel<CG, BK>;
+  using Cfg = TcCfg<CG>;
+  auto kern = gemm_tf32x3_kernel<CG>;
   AM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(args.tiles_m * args.tiles_n * CG), 1, 1);
@@ -334,23 +369,24 @@ static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int6
 static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const PackedF32& Q, float alpha,
                       float beta, float* C, int64_t strideP, int64_t strideQ) {
   if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
-  static int bk_env = -1;
-  if (bk_env < 0) { const char* e = getenv("AM_TC_BK"); bk_env = (e && atoi(e) == 16) ? 16 : 32; }
-  const int bk = bk_env;
+  static int flush_env = -1;
+  if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
+  const int bk = 32;
   CUtensorMap tms[4];
   int rc;
   if ((rc = make_tmap(&tms[0], P.hi, P.Rpad, P.Kpad, bk)) || (rc = make_tmap(&tms[1], P.lo, P.Rpad, P.Kpad, bk)) ||
       (rc = make_tmap(&tms[2], Q.hi, Q.Rpad, Q.Kpad, bk)) || (rc = make_tmap(&tms[3], Q.lo, Q.Rpad, Q.Kpad, bk)))
     return rc;
   TcArgs args;
-  args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk);
+  args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
+  args.tiles_n = (int)ceil_div(Q.R, 256);
   if (cta_group == 2) {
-    args.tiles_m = (int)ceil_div(P.R, 256); args.tiles_n = (int)ceil_div(Q.R, 512);
-    return bk == 32 ? launch_tc<2, 32>(st, tms, args) : launch_tc<2, 16>(st, tms, args);
+    args.tiles_m = (int)ceil_div(P.R, 256);
+    return launch_tc<2>(st, tms, args);
   }
-  args.tiles_m = (int)ceil_div(P.R, 128); args.tiles_n = (int)ceil_div(Q.R, 256);
-  return bk == 32 ? launch_tc<1, 32>(st, tms, args) : launch_tc<1, 16>(st, tms, args);
+  args.tiles_m = (int)ceil_div(P.R, 128);
+  return launch_tc<1>(st, tms, args);
 }
 
 int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,

@@ -93,20 +93,21 @@ def exp_simt_parity():
     return res
 
 
-def _tc_parity(path, bk):
-    os.environ["AM_TC_BK"] = str(bk)
+def _tc_parity(path, flush):
+    os.environ["AM_TC_FLUSH_KB"] = str(flush)
     res = {}
-    for (M, N, K) in [(128, 256, 32), (256, 512, 64), (512, 512, 256), (300, 700, 100), (1024, 2048, 1024)]:
+    for (M, N, K) in [(128, 256, 32), (256, 512, 64), (300, 700, 100), (1024, 2048, 1024), (512, 768, 4096), (512, 512, 16384)]:
         for lay in ("rr", "rrc", "cc"):
             res[f"{M}x{N}x{K}_{lay}"] = _parity("f32", M, N, K, path=path, layout=lay)
     res["alpha_beta"] = _parity("f32", 512, 512, 512, path=path, alpha=-3, beta=2)
     return res
 
 
-def exp_tc1_bk32(): return _tc_parity(3, 32)
-def exp_tc1_bk16(): return _tc_parity(3, 16)
-def exp_tc2_bk32(): return _tc_parity(2, 32)
-def exp_tc2_bk16(): return _tc_parity(2, 16)
+def exp_tc1_f2(): return _tc_parity(3, 2)
+def exp_tc2_f1(): return _tc_parity(2, 1)
+def exp_tc2_f2(): return _tc_parity(2, 2)
+def exp_tc2_f4(): return _tc_parity(2, 4)
+def exp_tc2_f8(): return _tc_parity(2, 8)
 
 
 def _gemm_speed(dt, n, path=None, reps=5):
@@ -134,18 +135,19 @@ def exp_simt_speed():
     return res
 
 
-def _tc_speed(path, bk):
-    os.environ["AM_TC_BK"] = str(bk)
+def _tc_speed(path, flush):
+    os.environ["AM_TC_FLUSH_KB"] = str(flush)
     res = {}
     for n in (4096, 8192, 16384):
         res[f"f32_{n}"] = _gemm_speed("f32", n, path=path, reps=3)
     return res
 
 
-def exp_tc1_speed_bk32(): return _tc_speed(3, 32)
-def exp_tc2_speed_bk32(): return _tc_speed(2, 32)
-def exp_tc2_speed_bk16(): return _tc_speed(2, 16)
-def exp_tc1_speed_bk16(): return _tc_speed(3, 16)
+def exp_tc1_speed_f2(): return _tc_speed(3, 2)
+def exp_tc2_speed_f1(): return _tc_speed(2, 1)
+def exp_tc2_speed_f2(): return _tc_speed(2, 2)
+def exp_tc2_speed_f4(): return _tc_speed(2, 4)
+def exp_tc2_speed_f8(): return _tc_speed(2, 8)
 
 
 def exp_conv_parity():
@@ -197,8 +199,8 @@ def exp_conv_speed():
     return res
 
 
-EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_bk32", "tc2_bk32", "tc1_bk16", "tc2_bk16", "simt_speed",
-               "tc1_speed_bk32", "tc2_speed_bk32", "tc2_speed_bk16", "tc1_speed_bk16", "conv_speed"]
+EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed",
+               "tc1_speed_f2", "tc2_speed_f1", "tc2_speed_f2", "tc2_speed_f4", "tc2_speed_f8", "conv_speed"]
 
 
 def main():

@@ -76,6 +76,7 @@ int sm_count() {
 }
 
 static std::atomic<int> g_f32_path{AM_F32_AUTO};
+static std::atomic<int> g_f64_path{AM_F64_AUTO};
 
 template <class T>
 static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, const T* B, T* C) {
@@ -201,7 +202,26 @@ int am_gemm_strided_f32(am_stream_t s, int64_t M, int64_t N, int64_t K, float al
     if (rc) return rc;                                                                                          \
     return gemm_simt<T>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);          \
   }
-DEF_GEMM_SIMT(f64, double)
+int am_set_f64_path(int path) {
+  if (path < AM_F64_AUTO || path > AM_F64_DMMA) { set_last_error("am_set_f64_path: bad selector"); return AM_ERR_INVALID; }
+  g_f64_path.store(path);
+  return AM_OK;
+}
+int am_get_f64_path(void) { return g_f64_path.load(); }
+
+int am_gemm_strided_f64(am_stream_t s, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t rsA,
+                        int64_t csA, const double* B, int64_t rsB, int64_t csB, double beta, double* C, int64_t rsC,
+                        int64_t csC) {
+  int rc = check_gemm_args(M, N, K, A, B, C);
+  if (rc == -1) return AM_OK;
+  if (rc) return rc;
+  const int path = g_f64_path.load();
+  // DMMA kernel has one 128x128 tile shape: use it once those tiles cover most of the chip
+  const bool big = ceil_div(M, 128) * ceil_div(N, 128) >= (2 * (int64_t)sm_count()) / 3;
+  if (path == AM_F64_DMMA || (path == AM_F64_AUTO && big))
+    return gemm_f64_dmma((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  return gemm_simt<double>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+}
 DEF_GEMM_SIMT(i32, int32_t)
 DEF_GEMM_SIMT(i64, int64_t)
 

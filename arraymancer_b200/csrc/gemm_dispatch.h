@@ -29,6 +29,11 @@ int packed_free_f32(void* handle);
 int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB, float beta, float* C, int64_t rsC,
                     int64_t csC);
 
+// gemm_f64_dmma.cu — FP64 tensor-pipe GEMM (mma.sync m8n8k4 f64), any strides
+int gemm_f64_dmma(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t rsA,
+                  int64_t csA, const double* B, int64_t rsB, int64_t csB, double beta, double* C, int64_t rsC,
+                  int64_t csC);
+
 // conv.cu
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,

@@ -76,6 +76,13 @@ enum { AM_F32_AUTO = 0, AM_F32_SIMT = 1, AM_F32_TC = 2, AM_F32_TC_1CTA = 3 };
 AM_API int am_set_f32_path(int path);
 AM_API int am_get_f32_path(void);
 
+/* Float64 path selector for am_gemm_strided_f64 (process-wide, default AM_F64_AUTO):
+ * AUTO = DMMA (mma.sync m8n8k4 f64, FP64 tensor pipe) once the output fills 128x128 tiles, DFMA
+ * SIMT kernel for small shapes; SIMT / DMMA force one kernel. */
+enum { AM_F64_AUTO = 0, AM_F64_SIMT = 1, AM_F64_DMMA = 2 };
+AM_API int am_set_f64_path(int path);
+AM_API int am_get_f64_path(void);
+
 /* ---- pre-packed float32 operands ---------------------------------------------------------
  * Device-side counterpart of laser's pre-packed GEMM API
  * (laser/primitives/matrix_multiplication/gemm_prepacked.nim:276-293 `gemm_packed`, with

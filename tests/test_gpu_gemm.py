@@ -163,6 +163,24 @@ def test_stride_variants(am, oracle, dt):
                     assert rel_fro(got, want) <= (F32_TOL if dt == "f32" else F64_TOL)
 
 
+@pytest.mark.parametrize("path", ["dmma", "simt"])
+def test_f64_both_kernels(am, oracle, path):
+    """float64 has two kernels (DMMA tensor pipe / DFMA SIMT); force each over odd shapes, layouts, alpha/beta."""
+    am.set_f64_path(am.F64_DMMA if path == "dmma" else am.F64_SIMT)
+    try:
+        for (M, N, K) in [(1, 1, 1), (7, 9, 5), (129, 130, 67), (300, 257, 1001), (1024, 1024, 512)]:
+            a, b = rand((M, K), "f64", 51), rand((K, N), "f64", 52)
+            check(am, oracle, "f64", a, b)
+            check(am, oracle, "f64", a, b, alpha=-3, beta=2, c0=rand((M, N), "f64", 53), c_order="F")
+        # transposed operand views
+        a, b = rand((200, 300), "f64", 54), rand((150, 300), "f64", 55)
+        C = torch.empty((200, 150), dtype=torch.float64, device="cuda")
+        am.gemm_strided(1, dev(a), dev(b).t(), 0, C)
+        assert rel_fro(C.cpu().numpy(), oracle.matmul(a, b.T)) <= F64_TOL
+    finally:
+        am.set_f64_path(am.F64_AUTO)
+
+
 def test_negative_strides_through_raw_capi(am, oracle):
     """torch cannot express negative strides, the C ABI can: call it with raw pointers."""
     import ctypes

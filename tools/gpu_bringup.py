@@ -150,6 +150,17 @@ def exp_tc2_speed_f4(): return _tc_speed(2, 4)
 def exp_tc2_speed_f8(): return _tc_speed(2, 8)
 
 
+def exp_f64_speed():
+    import arraymancer_b200 as am
+    res = {}
+    for name, path in (("dmma", am.F64_DMMA), ("simt", am.F64_SIMT)):
+        am.set_f64_path(path)
+        for n in (1500, 4096, 8192):
+            res[f"{name}_{n}"] = _gemm_speed("f64", n, reps=3)
+    am.set_f64_path(am.F64_AUTO)
+    return res
+
+
 def exp_conv_parity():
     import numpy as np
     import torch
@@ -199,7 +210,7 @@ def exp_conv_speed():
     return res
 
 
-EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed",
+EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed", "f64_speed",
                "tc1_speed_f2", "tc2_speed_f1", "tc2_speed_f2", "tc2_speed_f4", "tc2_speed_f8", "conv_speed"]
 
 

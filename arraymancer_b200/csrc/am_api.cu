@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "am_common.cuh"
 #include "gemm_dispatch.h"
@@ -103,7 +104,11 @@ static int gemm_f32_dispatch(cudaStream_t st, int64_t M, int64_t N, int64_t K, f
   return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
 }
 
-// host-buffer GEMM: what `a.cuda * b.cuda` then `.cpu` does (init_cuda.nim:23-59).
+// host-buffer GEMM: what `a.cuda * b.cuda` then `.cpu` does (init_cuda.nim:23-59), as one call.
+// Row-major-like A and C are processed in row chunks on three streams — H2D of chunk j+1, GEMM of chunk j and
+// D2H of chunk j-1 overlap — after B has been copied (and, for f32, split/packed) once.
+bool g_reuse_packed_b = false;   // read by gemm_f32_tc: B was packed by the previous chunk of this host call
+
 template <class T, class F>
 static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
                      int64_t csA, const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) {
@@ -121,29 +126,83 @@ static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, 
   extent(K, N, rsB, csB, &loB, &hiB);
   extent(M, N, rsC, csC, &loC, &hiC);
   const size_t nA = (size_t)(hiA - loA + 1), nB = (size_t)(hiB - loB + 1), nC = (size_t)(hiC - loC + 1);
-  cudaStream_t st = nullptr;
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+
+  int dev = 0;
+  AM_CUDA_TRY(cudaGetDevice(&dev));
+  static thread_local int pool_tuned_dev = -1;
+  if (pool_tuned_dev != dev) {       // keep freed blocks cached in the stream-ordered pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_tuned_dev = dev;
+  }
+  // row chunks: only when rows of A and of C are increasing, disjoint host ranges
+  const bool rowwise = rsA > 0 && csA > 0 && rsA >= csA * (K > 1 ? 1 : 0) && rsA >= (K - 1) * csA + 1 &&
+                       rsC > 0 && csC > 0 && rsC >= (N - 1) * csC + 1 && beta == T(0);
+  int64_t chunk = M;
+  if (rowwise && M >= 2048) {
+    chunk = ((M / 8 + 255) / 256) * 256;
+    if (chunk < 512) chunk = 512;
+  }
+  const int nchunks = (int)((M + chunk - 1) / chunk);
+
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> ev_in((size_t)nchunks, nullptr), ev_cmp((size_t)nchunks, nullptr);
+  cudaEvent_t ev_alloc = nullptr;
   T *dA = nullptr, *dB = nullptr, *dC = nullptr;
   int status = AM_OK;
+  cudaError_t e = cudaSuccess;
   do {
-    if (cudaMallocAsync(&dA, nA * sizeof(T), st) != cudaSuccess || cudaMallocAsync(&dB, nB * sizeof(T), st) != cudaSuccess ||
-        cudaMallocAsync(&dC, nC * sizeof(T), st) != cudaSuccess) { status = cuda_fail(cudaGetLastError(), "cudaMallocAsync"); break; }
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(dA, A + loA, nA * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dB, B + loB, nB * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess) { status = cuda_fail(e, "H2D"); break; }
-    if (beta != T(0) || nC != (size_t)(M * N)) {   // C is read, or the view has gaps that must survive the D2H copy
-      if ((e = cudaMemcpyAsync(dC, C + loC, nC * sizeof(T), cudaMemcpyHostToDevice, st)) != cudaSuccess) { status = cuda_fail(e, "H2D C"); break; }
+    if ((e = cudaMallocAsync(&dA, nA * sizeof(T), s_in)) != cudaSuccess || (e = cudaMallocAsync(&dB, nB * sizeof(T), s_in)) != cudaSuccess ||
+        (e = cudaMallocAsync(&dC, nC * sizeof(T), s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocAsync"); break; }
+    if ((e = cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+    if ((e = cudaMemcpyAsync(dB, B + loB, nB * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D B"); break; }
+    if (nchunks == 1) {
+      if ((e = cudaMemcpyAsync(dA, A + loA, nA * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A"); break; }
+      if (beta != T(0) || nC != (size_t)(M * N)) {   // C is read, or the view has gaps that must survive the D2H copy
+        if ((e = cudaMemcpyAsync(dC, C + loC, nC * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D C"); break; }
+      }
+      status = device_gemm(s_in, M, N, K, alpha, dA - loA, rsA, csA, dB - loB, rsB, csB, beta, dC - loC, rsC, csC);
+      if (status) break;
+      if ((e = cudaMemcpyAsync(C + loC, dC, nC * sizeof(T), cudaMemcpyDeviceToHost, s_in)) != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
+    } else {
+      cudaEventRecord(ev_alloc, s_in);                 // allocations are ordered on s_in
+      cudaStreamWaitEvent(s_out, ev_alloc, 0);
+      for (int j = 0; j < nchunks && !status; j++) {
+        const int64_t r0 = (int64_t)j * chunk, rows = (M - r0 < chunk) ? M - r0 : chunk;
+        const size_t a_elems = (size_t)((rows - 1) * rsA + (K - 1) * csA + 1);
+        const size_t c_elems = (size_t)((rows - 1) * rsC + (N - 1) * csC + 1);
+        if ((e = cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ev_cmp[j], cudaEventDisableTiming)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+        if ((e = cudaMemcpyAsync(dA + r0 * rsA, A + r0 * rsA, a_elems * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A chunk"); break; }
+        cudaEventRecord(ev_in[j], s_in);
+        cudaStreamWaitEvent(s_cmp, ev_in[j], 0);       // (also orders after the B copy, issued earlier on s_in)
+        g_reuse_packed_b = (j > 0);
+        status = device_gemm(s_cmp, rows, N, K, alpha, dA + r0 * rsA, rsA, csA, dB - loB, rsB, csB, beta, dC + r0 * rsC, rsC, csC);
+        g_reuse_packed_b = false;
+        if (status) break;
+        cudaEventRecord(ev_cmp[j], s_cmp);
+        cudaStreamWaitEvent(s_out, ev_cmp[j], 0);
+        if ((e = cudaMemcpyAsync(C + r0 * rsC, dC + r0 * rsC, c_elems * sizeof(T), cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) { status = cuda_fail(e, "D2H C chunk"); break; }
+      }
     }
-    status = device_gemm(st, M, N, K, alpha, dA - loA, rsA, csA, dB - loB, rsB, csB, beta, dC - loC, rsC, csC);
-    if (status) break;
-    if ((e = cudaMemcpyAsync(C + loC, dC, nC * sizeof(T), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { status = cuda_fail(e, "sync"); break; }
   } while (0);
-  if (dA) cudaFreeAsync(dA, st);
-  if (dB) cudaFreeAsync(dB, st);
-  if (dC) cudaFreeAsync(dC, st);
-  cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
+  if ((e = cudaStreamSynchronize(s_in)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if ((e = cudaStreamSynchronize(s_cmp)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if (dA) cudaFreeAsync(dA, s_in);
+  if (dB) cudaFreeAsync(dB, s_in);
+  if (dC) cudaFreeAsync(dC, s_in);
+  cudaStreamSynchronize(s_in);
+  for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
+  for (auto ev : ev_cmp) if (ev) cudaEventDestroy(ev);
+  if (ev_alloc) cudaEventDestroy(ev_alloc);
+  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
   return status;
 }
 

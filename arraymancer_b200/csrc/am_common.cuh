@@ -41,6 +41,30 @@ __device__ __forceinline__ T mac(T a, T b, T acc) {
     return (T)((U)acc + (U)a * (U)b);
   }
 }
+// int64 multiply-accumulate mod 2^64 in exactly three IMAD-class instructions
+// (IMAD.WIDE.U32 with 64-bit accumulate + two 32-bit IMADs into the high word); left to itself
+// nvcc emits five (separate 64-bit add), measured on the first GEMM profile (profiles/r01_*).
+template <>
+__device__ __forceinline__ int64_t mac<int64_t>(int64_t a, int64_t b, int64_t acc) {
+  const uint32_t alo = (uint32_t)a, ahi = (uint32_t)((uint64_t)a >> 32);
+  const uint32_t blo = (uint32_t)b, bhi = (uint32_t)((uint64_t)b >> 32);
+  uint64_t r;
+  asm("{\n\t.reg .u32 lo, hi;\n\t"
+      "mad.wide.u32 %0, %1, %2, %5;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "mad.lo.u32 hi, %1, %4, hi;\n\t"
+      "mad.lo.u32 hi, %3, %2, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}"
+      : "=l"(r) : "r"(alo), "r"(blo), "r"(ahi), "r"(bhi), "l"((uint64_t)acc));
+  return (int64_t)r;
+}
+// both operands known to fit in int32 (sign-extended): one IMAD.WIDE per multiply-accumulate, still exact mod 2^64
+__device__ __forceinline__ int64_t mac_narrow_i64(int64_t a, int64_t b, int64_t acc) {
+  int64_t r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"((int32_t)a), "r"((int32_t)b), "l"(acc));
+  return r;
+}
+
 template <class T>
 __device__ __forceinline__ T mul_nocontract(T a, T b) {
   if constexpr (std::is_same<T, float>::value) return __fmul_rn(a, b);
@@ -74,5 +98,6 @@ __device__ __forceinline__ T epilogue_value(T alpha, T ab, T beta, T cold) {
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 static inline int64_t iabs64(int64_t a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ int64_t iabs64_dev(int64_t a) { return a < 0 ? -a : a; }
 
 }  // namespace am

@@ -90,7 +90,7 @@ struct StridedEpilogue {   // gemm_ukernel_generic.nim:96-125 semantics on a str
 template <class T, class Cfg, class LA, class LB, class Epi>
 __global__ void __launch_bounds__(Cfg::NT)
 contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t k_per_split,
-                     int a_kfast, int b_kfast) {
+                     int a_kfast, int b_kfast, const int* __restrict__ wide_flag = nullptr) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN, V = Cfg::V;
   constexpr int TX = Cfg::TX, TY = Cfg::TY, NT = Cfg::NT, LDA = Cfg::LDA, LDB = Cfg::LDB;
   constexpr int EA = Cfg::EA, EB = Cfg::EB;
@@ -133,9 +133,26 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
   for (int i = 0; i < TM; i++)
 #pragma unroll
     for (int j = 0; j < TN; j++) acc[i][j] = T(0);
+  // float32 only: two-level accumulation with the reference's K blocking (kc = 512 for 4-byte types,
+  // gemm_tiling.nim:310): fma-sequential inside a 512-deep block, blocks added in order — the same order
+  // as laser's `C += AB_block` (gemm.nim:158-166), which keeps the error from growing like sqrt(K).
+  constexpr bool kTwoLevel = std::is_same<T, float>::value;
+  constexpr int kFlushTiles = 512 / BK;
+  T acc2[kTwoLevel ? TM : 1][kTwoLevel ? TN : 1];
+  if constexpr (kTwoLevel) {
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) acc2[i][j] = T(0);
+  }
+  int flush_cnt = 0;
 
   T ra[EA], rb[EB];
   const int64_t ntiles = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+  // int64 only: a pre-pass (gemm_simt.cu::i64_range_kernel) found every operand element inside the
+  // int32 range -> one IMAD.WIDE per multiply-accumulate instead of three IMADs, same bits.
+  bool narrow = false;
+  if constexpr (std::is_same<T, int64_t>::value) narrow = (wide_flag != nullptr) && (*wide_flag == 0);
 
   if (ntiles > 0) {
 #pragma unroll
@@ -171,10 +188,28 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
 #pragma unroll
       for (int g = 0; g < TN / V; g++)
         fb.q[g] = *reinterpret_cast<const Vec*>(&Bs[buf][kk][g * (TX * V) + tx * V]);
+      if constexpr (std::is_same<T, int64_t>::value) {
+        if (narrow) {
+#pragma unroll
+          for (int i = 0; i < TM; i++)
+#pragma unroll
+            for (int j = 0; j < TN; j++) acc[i][j] = mac_narrow_i64(fa.e[i], fb.e[j], acc[i][j]);
+          continue;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < TM; i++)
 #pragma unroll
         for (int j = 0; j < TN; j++) acc[i][j] = mac<T>(fa.e[i], fb.e[j], acc[i][j]);
+    }
+    if constexpr (kTwoLevel) {
+      if (++flush_cnt == kFlushTiles) {
+        flush_cnt = 0;
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+          for (int j = 0; j < TN; j++) { acc2[i][j] = __fadd_rn(acc2[i][j], acc[i][j]); acc[i][j] = T(0); }
+      }
     }
     if (more) {
       T* a1 = &As[buf ^ 1][0][0];
@@ -185,6 +220,13 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
       for (int i = 0; i < EB; i++) b1[ob[i]] = rb[i];
     }
     __syncthreads();
+  }
+
+  if constexpr (kTwoLevel) {
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) acc[i][j] = __fadd_rn(acc2[i][j], acc[i][j]);
   }
 
   // ---- epilogue: thread owns rows g*(TY*V)+ty*V+v, column groups h*(TX*V)+tx*V..+V

@@ -27,6 +27,8 @@
 
 namespace am {
 
+extern bool g_reuse_packed_b;   // am_api.cu: set while a host-buffer GEMM iterates over row chunks
+
 // ------------------------------------------------------------------ split / pack pre-pass
 // out planes: [Rpad][Kpad] row-major (K contiguous).  (r, k) of X at X[r*r_stride + k*k_stride].
 __global__ void __launch_bounds__(256)
@@ -404,7 +406,13 @@ int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K,
   if (rc) return rc;
   pa.hi = (float*)wsA; pa.lo = pa.hi + pa.Rpad * pa.Kpad;
   pb.hi = (float*)wsB; pb.lo = pb.hi + pb.Rpad * pb.Kpad;
-  if ((rc = pack_into(st, A, M, K, rsA, csA, &pa)) || (rc = pack_into(st, B, N, K, csB, rsB, &pb))) return rc;
+  // inside one am_host_gemm_strided_f32 call B is packed by the first row chunk and reused by the rest
+  static thread_local struct { const float* B; int64_t N, K, rs, cs; float* ws; } last_b = {nullptr, 0, 0, 0, 0, nullptr};
+  const bool reuse_b = g_reuse_packed_b && last_b.B == B && last_b.N == N && last_b.K == K && last_b.rs == rsB &&
+                       last_b.cs == csB && last_b.ws == pb.hi;
+  if ((rc = pack_into(st, A, M, K, rsA, csA, &pa))) return rc;
+  if (!reuse_b && (rc = pack_into(st, B, N, K, csB, rsB, &pb))) return rc;
+  last_b = {B, N, K, rsB, csB, pb.hi};
   // The epilogue's lanes run along the P rows (TMEM lanes): make that C's unit-stride dimension.
   // Column-major C (rs == 1, the CudaTensor default): P = A.  Row-major C: C^T = B^T A^T, P = B.
   if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, cta_group, pa, pb, alpha, beta, C, rsC, csC);

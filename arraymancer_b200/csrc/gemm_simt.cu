@@ -15,6 +15,41 @@ struct GemmCfgs {
   using Big = SimtCfg<T, 128, 128, BK, 8, 8>;     // 256 threads, 8x8 register tile
   using Small = SimtCfg<T, 64, 64, BK, 4, 4>;     // 256 threads, 4x4 register tile
 };
+// int64: a multiply-accumulate is three dependent IMADs, shared memory is nowhere near the limit, so a
+// 4x8 register tile (half the accumulator registers) with 512 threads doubles the resident warps per
+// scheduler (latency hiding) at the same 128x128 CTA tile.
+template <>
+struct GemmCfgs<int64_t> {
+  static constexpr int BK = 8;
+  using Big = SimtCfg<int64_t, 128, 128, BK, 4, 8>;   // 512 threads, 4x8 register tile
+  using Small = SimtCfg<int64_t, 64, 64, BK, 4, 4>;
+};
+
+// Pre-pass of the int64 GEMM: is every element of A and of B representable in int32?  (flag := 1 if not.)
+// O(MK + KN) reads; lets the mainloop use one IMAD.WIDE per multiply-accumulate (bit-identical result).
+__global__ void i64_range_kernel(const int64_t* __restrict__ A, int64_t a_mn, int64_t a_k, int64_t M,
+                                 const int64_t* __restrict__ B, int64_t b_mn, int64_t b_k, int64_t N, int64_t K,
+                                 int* __restrict__ wide_flag) {
+  const bool isB = blockIdx.y == 1;
+  const int64_t* X = isB ? B : A;
+  const int64_t mn_stride = isB ? b_mn : a_mn, k_stride = isB ? b_k : a_k, MN = isB ? N : M;
+  const bool k_fast = iabs64_dev(k_stride) <= iabs64_dev(mn_stride);
+  const int64_t inner = k_fast ? K : MN, total = MN * K;
+  bool wide = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = i / inner, in = i - o * inner;
+    const int64_t v = k_fast ? X[o * mn_stride + in * k_stride] : X[in * mn_stride + o * k_stride];
+    wide |= (v != (int64_t)(int32_t)v);
+  }
+  if (__any_sync(0xffffffffu, wide) && (threadIdx.x & 31) == 0) atomicOr(wide_flag, 1);
+}
+
+template <>
+struct GemmCfgs<int32_t> {
+  static constexpr int BK = 16;
+  using Big = SimtCfg<int32_t, 128, 128, BK, 4, 8>;   // 512 threads: IMAD issues at half the FFMA rate, occupancy wins
+  using Small = SimtCfg<int32_t, 64, 64, BK, 4, 4>;
+};
 
 template <class T, class Cfg>
 static int launch_cfg(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t a_mn,
@@ -39,7 +74,22 @@ static int launch_cfg(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha,
     }
     return AM_OK;
   }
-  contract_simt_kernel<T, Cfg, LA, LA, Epi><<<grid, Cfg::NT, 0, st>>>(la, lb, epi, K, K, a_kfast, b_kfast);
+  const int* wide_flag = nullptr;
+  if constexpr (std::is_same<T, int64_t>::value) {
+    if (2.0 * (double)M * (double)N * (double)K >= 2.0e8) {
+      // flags live in a small ring so back-to-back calls on different streams do not share one
+      static std::atomic<unsigned> ring{0};
+      void* base = nullptr;
+      int rc = workspace(kWsMisc, 64 * sizeof(int) + 1024, &base);
+      if (rc) return rc;
+      int* flag = (int*)base + (ring++ % 64);
+      AM_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      i64_range_kernel<<<dim3((unsigned)(4 * sm_count()), 2), 256, 0, st>>>(A, a_mn, a_k, M, B, b_mn, b_k, N, K, flag);
+      g_launch_count++;
+      wide_flag = flag;
+    }
+  }
+  contract_simt_kernel<T, Cfg, LA, LA, Epi><<<grid, Cfg::NT, 0, st>>>(la, lb, epi, K, K, a_kfast, b_kfast, wide_flag);
   g_launch_count++;
   AM_CUDA_TRY(cudaGetLastError());
   return AM_OK;

@@ -7,6 +7,23 @@
 
 namespace am {
 
+template <int CHAINS>
+__global__ void __launch_bounds__(256) i64_narrow_peak_kernel(int64_t* out, int iters, int64_t a0, int64_t b0) {
+  int64_t acc[CHAINS];
+  int64_t a = a0 + threadIdx.x, b = b0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) acc[i] = i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) acc[i] = mac_narrow_i64(a, b, acc[i]);
+    a = (int32_t)(a + acc[0]);
+  }
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  if (s == 123457) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class T, int CHAINS>
 __global__ void __launch_bounds__(256) simt_peak_kernel(T* out, int iters, T a0, T b0) {
   T acc[CHAINS];
@@ -114,7 +131,7 @@ int microbench(int which, double* tops) {
   if (!tops) { set_last_error("microbench: null output"); return AM_ERR_INVALID; }
   const int sms = sm_count();
   void* scratch = nullptr;
-  int rc = workspace(kWsMisc, (size_t)sms * 8 * 256 * 8, &scratch);
+  int rc = workspace(kWsConv, (size_t)sms * 8 * 256 * 8, &scratch);
   if (rc) return rc;
   float ms = 0;
   const int blocks = sms * 8, threads = 256;
@@ -145,6 +162,11 @@ int microbench(int which, double* tops) {
       const int iters = 1 << 12;
       rc = time_launch([&] { dmma_peak_kernel<8><<<blocks, threads>>>((double*)scratch, iters); g_launch_count++; }, 3, &ms);
       ops = 2.0 * 256.0 * 8 * (double)iters * blocks * (threads / 32);
+    } break;
+    case 7: {
+      const int iters = 1 << 14;
+      rc = time_launch([&] { i64_narrow_peak_kernel<CH><<<blocks, threads>>>((int64_t*)scratch, iters, 3, 5); g_launch_count++; }, 3, &ms);
+      ops = 2.0 * CH * (double)iters * blocks * threads;
     } break;
     case 5:
     case 6: {

@@ -51,13 +51,19 @@ def gemm_strided(alpha, A: torch.Tensor, B: torch.Tensor, beta, C: torch.Tensor)
         raise IndexError(f"gemm_strided: shape mismatch {tuple(A.shape)} * {tuple(B.shape)} -> {tuple(C.shape)}")
     if not (A.is_cuda and B.is_cuda and C.is_cuda):
         raise ValueError("gemm_strided: operands must live on the GPU (no CPU fallback)")
-    suf = _SUFFIX[A.dtype]
-    ct = _capi.CTYPE[suf]
-    with torch.cuda.device(C.device):
-        _capi.check(getattr(_capi.lib(), f"am_gemm_strided_{suf}")(
-            _stream_ptr(C), M, N, K, ct(alpha), A.data_ptr(), A.stride(0), A.stride(1),
-            B.data_ptr(), B.stride(0), B.stride(1), ct(beta), C.data_ptr(), C.stride(0), C.stride(1)))
+    _gemm_raw(_SUFFIX[A.dtype], C.device, M, N, K, alpha, (A.data_ptr(), A.stride(0), A.stride(1)),
+              (B.data_ptr(), B.stride(0), B.stride(1)), beta, (C.data_ptr(), C.stride(0), C.stride(1)))
     return C
+
+
+def _gemm_raw(suf, device, M, N, K, alpha, a, b, beta, c) -> None:
+    """The C-ABI call itself: a, b, c are (device pointer to the first logical element, rowStride,
+    colStride) — what Nim passes as (get_offset_ptr, strides[0], strides[1]); strides may be negative."""
+    ct = _capi.CTYPE[suf]
+    with torch.cuda.device(device):
+        _capi.check(getattr(_capi.lib(), f"am_gemm_strided_{suf}")(
+            torch.cuda.current_stream(device).cuda_stream, M, N, K, ct(alpha), a[0], a[1], a[2],
+            b[0], b[1], b[2], ct(beta), c[0], c[1], c[2]))
 
 
 def cublas_gemm(transa: int, transb: int, m: int, n: int, k: int, alpha, A: torch.Tensor, lda: int,
@@ -105,8 +111,12 @@ class CudaTensor:
         return len(self.shape)
 
     def view(self) -> torch.Tensor:
-        """The strided torch view (pointer + strides carrier)."""
+        """The strided torch view (only for non-negative strides; torch cannot express the others)."""
         return torch.as_strided(self.storage, self.shape, self.strides, self.offset)
+
+    def offset_ptr(self) -> int:
+        """get_offset_ptr (tensor/data_structure.nim:193-198): device address of the first logical element."""
+        return self.storage.data_ptr() + self.offset * self.storage.element_size()
 
     def cpu(self) -> np.ndarray:
         """Blocking D2H copy of the whole storage, keeping the strides (init_cuda.nim:43-59)."""
@@ -172,7 +182,14 @@ def gemm(alpha, A: CudaTensor, B: CudaTensor, beta, C: CudaTensor) -> None:
     """C = alpha*A*B + beta*C (tensor/operators_blas_l2l3.nim:58-81; cudaMM_C_eq_aAB_p_bC)."""
     if A.rank != 2 or B.rank != 2 or C.rank != 2:
         raise ValueError("gemm: inputs must be matrices")
-    gemm_strided(alpha, A.view(), B.view(), beta, C.view())
+    if A.dtype not in _SUFFIX or B.dtype != A.dtype or C.dtype != A.dtype:
+        raise TypeError("gemm: operands must share one of float32/float64/int32/int64")
+    M, K = A.shape
+    K2, N = B.shape
+    if K != K2 or C.shape != (M, N):
+        raise IndexError(f"gemm: shape mismatch {A.shape} * {B.shape} -> {C.shape}")   # check_matmat
+    _gemm_raw(_SUFFIX[A.dtype], C.storage.device, M, N, K, alpha, (A.offset_ptr(), A.strides[0], A.strides[1]),
+              (B.offset_ptr(), B.strides[0], B.strides[1]), beta, (C.offset_ptr(), C.strides[0], C.strides[1]))
 
 
 def matmul(a: CudaTensor, b: CudaTensor) -> CudaTensor:

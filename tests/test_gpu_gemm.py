@@ -137,11 +137,11 @@ def test_stride_variants(am, oracle, dt):
     """row-major, col-major, transposed, step-2 slices, negative steps, stride-0 broadcast — every
     (rowStride, colStride) pattern the reference's callers produce."""
     M, N, K = 37, 29, 150
-    ap, bp = rand((2 * M, 2 * K), dt, 11), rand((2 * K, 2 * N), dt, 12)
+    ap, bp = rand((2 * K, 2 * K), dt, 11), rand((2 * K, 2 * K), dt, 12)      # parents big enough for every view
     Ap, Bp = dev(ap), dev(bp)
-    a_views = [lambda x: x[:M, :K], lambda x: x[::2, ::2], lambda x: x[:K, :M].T, lambda x: x[M - 1::-1, :K] if isinstance(x, np.ndarray) else x[:M, :K].flip(0),
+    a_views = [lambda x: x[:M, :K], lambda x: x[:2 * M:2, ::2], lambda x: x[:K, :M].T, lambda x: x[M - 1::-1, :K] if isinstance(x, np.ndarray) else x[:M, :K].flip(0),
                lambda x: (np.broadcast_to(x[0:1, :K], (M, K)) if isinstance(x, np.ndarray) else x[0:1, :K].expand(M, K))]
-    b_views = [lambda x: x[:K, :N], lambda x: x[1::2, ::2][:K], lambda x: x[:N, :K].T]
+    b_views = [lambda x: x[:K, :N], lambda x: x[1::2, ::2][:K, :N], lambda x: x[:N, :K].T]
     for ai, av in enumerate(a_views):
         for bv in b_views:
             a_np, b_np = av(ap), bv(bp)
@@ -294,7 +294,8 @@ def test_c3_float32_16384_views_sampled(am, oracle):
     Cf = torch.empty((n, n), device="cuda").t()
     am.gemm_strided(1, P, Q, 0, Cf)
     am.gemm_strided(1, P, Q, 0, C)
-    assert torch.equal(Cf, C)                      # same arithmetic, different store layout
+    # the operand roles (TMEM lanes vs columns) swap with C's layout, so the roundings differ: not bit-equal
+    assert rel_fro(Cf[rt].cpu().numpy(), C[rt].cpu().numpy()) <= 2e-6
 
 
 def test_integer_linearity_at_full_size(am):

@@ -34,7 +34,7 @@ def _time_gpu(fn, warm=2, reps=5):
 
 def exp_peaks():
     from arraymancer_b200 import _capi
-    names = ["ffma_f32", "dfma_f64", "imad_i32", "i64_mac", "dmma_f64", "umma_tf32_1cta", "umma_tf32_2cta"]
+    names = ["ffma_f32", "dfma_f64", "imad_i32", "i64_mac", "dmma_f64", "umma_tf32_1cta", "umma_tf32_2cta", "i64_narrow_mac"]
     res = {}
     for i, n in enumerate(names):
         try:

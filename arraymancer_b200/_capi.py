@@ -20,7 +20,7 @@ CTYPE = {"f32": ctypes.c_float, "f64": ctypes.c_double, "i32": ctypes.c_int32, "
 
 # every symbol include/am_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
-    ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path",
+    ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path", "am_set_conv_path",
      "am_cublas_gemm_f32", "am_cublas_gemm_f64", "am_pack_f32_a", "am_pack_f32_b", "am_repack_f32_a",
      "am_repack_f32_b", "am_gemm_packed_f32", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench"]
     + [f"am_gemm_strided_{s}" for s in SUFFIXES]
@@ -61,6 +61,7 @@ def lib() -> ctypes.CDLL:
     L.am_device_info.argtypes = [ctypes.POINTER(ci)] * 3
     L.am_set_f32_path.argtypes = [ci]
     L.am_set_f64_path.argtypes = [ci]
+    L.am_set_conv_path.argtypes = [ci]
     L.am_kernel_launch_count.restype = i64
     L.am_microbench.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     L.am_conv2d_out_dims.argtypes = [ctypes.POINTER(ConvDesc), ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -106,6 +107,13 @@ def set_f32_path(path: int) -> None:
 
 def set_f64_path(path: int) -> None:
     check(lib().am_set_f64_path(path))
+
+
+CONV_AUTO, CONV_GATHER = 0, 1
+
+
+def set_conv_path(path: int) -> None:
+    check(lib().am_set_conv_path(path))
 
 
 def kernel_launch_count() -> int:

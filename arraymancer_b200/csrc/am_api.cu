@@ -321,6 +321,12 @@ int am_packed_free_f32(am_packed_f32* h) { return packed_free_f32(h); }
 DEF_CUBLAS(f32, float)
 DEF_CUBLAS(f64, double)
 
+int am_set_conv_path(int path) {
+  if (path != AM_CONV_AUTO && path != AM_CONV_GATHER) { set_last_error("am_set_conv_path: bad selector"); return AM_ERR_INVALID; }
+  am::g_conv_path.store(path);
+  return AM_OK;
+}
+
 int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
   if (!d || d->strideH <= 0 || d->strideW <= 0 || d->dilH <= 0 || d->dilW <= 0) { set_last_error("conv2d_out_dims: bad descriptor"); return AM_ERR_INVALID; }
   if (Ho) *Ho = (d->H + 2 * d->padH - (d->dilH * (d->kH - 1) + 1)) / d->strideH + 1;

@@ -10,6 +10,8 @@
 //   wgrad    (conv.nim:140)      gW[co,k]      = sum_{n,p} gout[n,co,p] * im2col(in[n])[k,p]
 //       GEMM view: M = Cout, N = C*kH*kW (+1 ones-column = grad_bias, nnp_convolution.nim:94),
 //                  K = Nimg*Ho*Wo split over CTAs, fixed-order second pass (deterministic).
+#include <cstdlib>
+
 #include "contract_simt.cuh"
 #include "gemm_dispatch.h"
 
@@ -292,6 +294,16 @@ static int launch_by_rows(cudaStream_t st, const LA& la, const LB& lb, const Epi
   return launch<T, typename ConvCfgs<T>::C128>(st, la, lb, epi, M, N, K, 1, K);
 }
 
+// conv_direct.cu: shared-memory-staged direct kernels (fast path); *done == false -> use the gather kernels here
+template <class T>
+int conv2d_forward_direct(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const T* input,
+                          const T* kernel, const T* bias, T* output, bool* done);
+template <class T>
+int conv2d_dgrad_direct(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const T* grad_output,
+                        const T* kernel, T* grad_input, bool* done);
+std::atomic<int> g_conv_path{AM_CONV_AUTO};
+static bool direct_enabled() { return g_conv_path.load() == AM_CONV_AUTO; }
+
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
                    T* output) {
@@ -299,6 +311,11 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   if (!make_geom(d, &g)) { set_last_error("conv2d_forward: invalid geometry"); return AM_ERR_INVALID; }
   if (g.Nimg == 0) return AM_OK;
   if (!input || !kernel || !output) { set_last_error("conv2d_forward: null pointer"); return AM_ERR_INVALID; }
+  if (direct_enabled()) {
+    bool done = false;
+    int rcd = conv2d_forward_direct<T>(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
+    if (rcd || done) return rcd;
+  }
   int2 *tabF, *tabD, *tabW;
   int rc = get_tables(st, d, g, &tabF, &tabD, &tabW);
   if (rc) return rc;
@@ -325,7 +342,12 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
   int rc = get_tables(st, d, g, &tabF, &tabD, &tabW);
   if (rc) return rc;
 
-  if (grad_input && g.Nimg > 0) {          // dgrad
+  bool dgrad_done = false;
+  if (grad_input && g.Nimg > 0 && direct_enabled()) {
+    rc = conv2d_dgrad_direct<T>(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+    if (rc) return rc;
+  }
+  if (grad_input && g.Nimg > 0 && !dgrad_done) {          // dgrad, gather form (any stride)
     WeightTLoader<T> la{kernel, tabW, g, KD};
     GradOutColsLoader<T> lb{grad_output, tabD, g, NQ, KD};
     NchwEpilogue<T> epi{grad_input, nullptr, g.C, g.HW, NQ,

@@ -10,6 +10,7 @@
 namespace am {
 
 extern std::atomic<int64_t> g_launch_count;
+extern std::atomic<int> g_conv_path;          // conv.cu: AM_CONV_AUTO / AM_CONV_GATHER
 
 // gemm_simt.cu — strided SIMT GEMM, any layout
 template <class T>

@@ -28,6 +28,17 @@ METRIC = "sgemm_gflops"
 UNIT = "GFLOP/s"
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -111,7 +122,7 @@ def run_reference(args):
                              "sample": f"rows 0..{rows - 1} of A against the full {n}x{n} B (full N and K), restated laser "
                                        f"gemm_strided f32 AVX2+FMA 6x16 micro-kernel, OpenMP {threads} threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -120,13 +131,18 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=32768, help="square size (BASELINE configs[4]: 32768)")
+    ap.add_argument("--size", dest="n", type=int, default=32768, help="square size (BASELINE configs[4]: 32768)")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks per rank for compute/all-gather overlap (N>1)")
     ap.add_argument("--cpu-rows", type=int, default=768, help="rows of A in the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="check the gathered C against a local recomputation of sampled rows of every rank")
     args = ap.parse_args()
+    # NCCL prints a version banner on stdout at communicator creation: keep stdout clean for the ONE JSON line
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
@@ -221,6 +237,24 @@ def main():
     flops_step = 2.0 * n * n * n
     value = flops_step / (ms_per_step * 1e-3) / 1e9
 
+    verify = None
+    if args.verify:
+        # every rank recomputes 64 rows of every rank's first chunk from that rank's seed and compares with the gathered C
+        worst = 0.0
+        for r in range(world):
+            gr = torch.Generator(device=dev); gr.manual_seed(1234 + 7919 * r)
+            Ar = torch.rand((rows_local, n), device=dev, dtype=torch.float32, generator=gr) * 2 - 1
+            ref = torch.empty((64, n), device=dev, dtype=torch.float32)
+            am.gemm_strided(1, Ar[:64], B, 0, ref)
+            lo = r * mc
+            got = C[lo:lo + 64]
+            worst = max(worst, float(((got - ref).double().norm() / ref.double().norm()).item()))
+            del Ar
+        tv = torch.tensor([worst], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        verify = {"max_rel_fro_vs_single_gpu_rows": float(tv.item()), "ok": bool(tv.item() <= 1e-6)}
+
     # ---- e2e: same job through the host-buffer C-ABI entry (pinned host memory, copies inside the region)
     e2e = None
     if not args.no_e2e:
@@ -286,6 +320,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if verify:
+        line["verify"] = verify
     if world == 1 and not args.no_cpu:
         # CPU baseline: restated laser gemm_strided on the host cores, bounded row sample of the same problem
         from oracle import laser_oracle as orc
@@ -302,7 +338,7 @@ def main():
                                 "kind": "port", "seconds": cs,
                                 "sample": f"rows 0..{rows - 1} of A against the full {n}x{n} B (full N and K); restated laser "
                                           "gemm_strided f32 (AVX2+FMA 6x16 micro-kernel, OpenMP), not a Nim build"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -133,6 +133,11 @@ typedef struct am_conv2d_desc {
 } am_conv2d_desc;
 
 AM_API int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo);
+/* Conv kernel selector (process-wide, default AM_CONV_AUTO): AUTO = shared-memory-staged direct kernel for
+ * forward and stride-1 data gradient when the tiles fit, generic gather kernel otherwise; GATHER forces the
+ * generic implicit-GEMM gather kernels everywhere (fallback / comparison). */
+enum { AM_CONV_AUTO = 0, AM_CONV_GATHER = 1 };
+AM_API int am_set_conv_path(int path);
 
 #define AM_DECL_CONV(SUF, T)                                                                     \
   AM_API int am_conv2d_forward_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input, \

@@ -89,12 +89,24 @@ CASES = [  # input, kernel, padding, stride, dilation
     ((1, 130, 6, 6), (6, 130, 3, 3), (1, 0), (2, 2), (2, 1)),      # > 128 input channels
     ((5, 2, 7, 7), (3, 2, 1, 1), (0, 0), (1, 1), (1, 1)),          # 1x1 kernel
     ((1, 1, 5, 5), (1, 1, 5, 5), (0, 0), (1, 1), (1, 1)),          # single output pixel
+    ((3, 5, 40, 37), (9, 5, 3, 3), (1, 1), (1, 1), (1, 1)),        # several row bands / images per CTA
+    ((2, 3, 9, 9), (4, 3, 3, 3), (3, 3), (1, 1), (1, 1)),          # padding larger than the kernel reach
+    ((70, 2, 6, 6), (3, 2, 3, 3), (1, 1), (1, 1), (1, 1)),         # many small images per CTA
 ]
+
+
+@pytest.fixture(params=["auto", "gather"])
+def conv_path(request, am):
+    """Both kernel families: the smem-staged direct kernels (AUTO) and the generic gather kernels (fallback)."""
+    from arraymancer_b200 import _capi
+    _capi.set_conv_path(_capi.CONV_GATHER if request.param == "gather" else _capi.CONV_AUTO)
+    yield request.param
+    _capi.set_conv_path(_capi.CONV_AUTO)
 
 
 @pytest.mark.parametrize("dt", ["f32", "f64", "i32", "i64"])
 @pytest.mark.parametrize("ci", range(len(CASES)))
-def test_forward_backward_vs_oracle(am, oracle, dt, ci):
+def test_forward_backward_vs_oracle(am, oracle, conv_path, dt, ci):
     xs, ks, pad, st, dil = CASES[ci]
     rng = np.random.default_rng(100 + ci)
     if dt.startswith("f"):

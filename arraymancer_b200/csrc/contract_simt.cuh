@@ -51,7 +51,25 @@ struct StridedLoader {
   __device__ __forceinline__ T load(const Slot& s, int64_t kt) const {
     return (s.ok && kt + s.k < Kend) ? s.ptr[kt * k_stride] : T(0);
   }
+  // cp.async staging: source address + validity (invalid -> zero fill, the address is not dereferenced)
+  static constexpr bool kAsync = true;
+  __device__ __forceinline__ const T* addr(const Slot& s, int64_t kt, bool* ok) const {
+    *ok = s.ok && kt + s.k < Kend;
+    return *ok ? s.ptr + kt * k_stride : p;
+  }
 };
+
+template <class L, class = void> struct LoaderIsAsync { static constexpr bool value = false; };
+template <class L> struct LoaderIsAsync<L, typename std::enable_if<L::kAsync>::type> { static constexpr bool value = true; };
+
+// global -> shared without a register round trip (LDGSTS); src_bytes = 0 zero-fills the destination
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst_smem, const void* src, bool ok) {
+  const int src_bytes = ok ? BYTES : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst_smem), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------- epilogues
 // Epilogue concept: void store(int64_t m, int64_t n0, const T (&v)[V], int z) — V consecutive
@@ -147,37 +165,13 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
   }
   int flush_cnt = 0;
 
-  T ra[EA], rb[EB];
   const int64_t ntiles = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
   // int64 only: a pre-pass (gemm_simt.cu::i64_range_kernel) found every operand element inside the
   // int32 range -> one IMAD.WIDE per multiply-accumulate instead of three IMADs, same bits.
   bool narrow = false;
   if constexpr (std::is_same<T, int64_t>::value) narrow = (wide_flag != nullptr) && (*wide_flag == 0);
 
-  if (ntiles > 0) {
-#pragma unroll
-    for (int i = 0; i < EA; i++) ra[i] = la.load(sa[i], kbeg);
-#pragma unroll
-    for (int i = 0; i < EB; i++) rb[i] = lb.load(sb[i], kbeg);
-    T* a0 = &As[0][0][0];
-    T* b0 = &Bs[0][0][0];
-#pragma unroll
-    for (int i = 0; i < EA; i++) a0[oa[i]] = ra[i];
-#pragma unroll
-    for (int i = 0; i < EB; i++) b0[ob[i]] = rb[i];
-  }
-  __syncthreads();
-
-  for (int64_t t = 0; t < ntiles; t++) {
-    const int buf = (int)(t & 1);
-    const bool more = (t + 1 < ntiles);
-    if (more) {      // global -> registers for the next tile while this one is consumed
-      const int64_t kt = kbeg + (t + 1) * BK;
-#pragma unroll
-      for (int i = 0; i < EA; i++) ra[i] = la.load(sa[i], kt);
-#pragma unroll
-      for (int i = 0; i < EB; i++) rb[i] = lb.load(sb[i], kt);
-    }
+  auto compute_tile = [&](int buf) {
 #pragma unroll
     for (int kk = 0; kk < BK; kk++) {
       union { Vec q[TM / V]; T e[TM]; } fa;
@@ -211,15 +205,72 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
           for (int j = 0; j < TN; j++) { acc2[i][j] = __fadd_rn(acc2[i][j], acc[i][j]); acc[i][j] = T(0); }
       }
     }
-    if (more) {
-      T* a1 = &As[buf ^ 1][0][0];
-      T* b1 = &Bs[buf ^ 1][0][0];
+  };
+
+  if constexpr (LoaderIsAsync<LA>::value && LoaderIsAsync<LB>::value) {
+    // ---- cp.async (LDGSTS) staging: tile t+1 streams into the other buffer while tile t is consumed; no
+    //      staging registers (the register-staged version had its loads sunk next to the STS by ptxas under the
+    //      128-register cap: 14 % of all stall samples on that one STS, profiles/r01_bringup.md)
+    const uint32_t as_base = (uint32_t)__cvta_generic_to_shared(&As[0][0][0]);
+    const uint32_t bs_base = (uint32_t)__cvta_generic_to_shared(&Bs[0][0][0]);
+    auto issue = [&](int buf, int64_t kt) {
 #pragma unroll
-      for (int i = 0; i < EA; i++) a1[oa[i]] = ra[i];
+      for (int i = 0; i < EA; i++) {
+        bool ok;
+        const T* src = la.addr(sa[i], kt, &ok);
+        cp_async_zfill<(int)sizeof(T)>(as_base + (uint32_t)((buf * BK * LDA + oa[i]) * sizeof(T)), src, ok);
+      }
 #pragma unroll
-      for (int i = 0; i < EB; i++) b1[ob[i]] = rb[i];
+      for (int i = 0; i < EB; i++) {
+        bool ok;
+        const T* src = lb.addr(sb[i], kt, &ok);
+        cp_async_zfill<(int)sizeof(T)>(bs_base + (uint32_t)((buf * BK * LDB + ob[i]) * sizeof(T)), src, ok);
+      }
+      cp_async_commit();
+    };
+    if (ntiles > 0) issue(0, kbeg);
+    for (int64_t t = 0; t < ntiles; t++) {
+      cp_async_wait_all();
+      __syncthreads();          // tile t visible to all; everyone is done reading the other buffer (tile t-1)
+      if (t + 1 < ntiles) issue((int)((t + 1) & 1), kbeg + (t + 1) * BK);
+      compute_tile((int)(t & 1));
+    }
+  } else {
+    T ra[EA], rb[EB];
+    if (ntiles > 0) {
+#pragma unroll
+      for (int i = 0; i < EA; i++) ra[i] = la.load(sa[i], kbeg);
+#pragma unroll
+      for (int i = 0; i < EB; i++) rb[i] = lb.load(sb[i], kbeg);
+      T* a0 = &As[0][0][0];
+      T* b0 = &Bs[0][0][0];
+#pragma unroll
+      for (int i = 0; i < EA; i++) a0[oa[i]] = ra[i];
+#pragma unroll
+      for (int i = 0; i < EB; i++) b0[ob[i]] = rb[i];
     }
     __syncthreads();
+    for (int64_t t = 0; t < ntiles; t++) {
+      const int buf = (int)(t & 1);
+      const bool more = (t + 1 < ntiles);
+      if (more) {      // global -> registers for the next tile while this one is consumed
+        const int64_t kt = kbeg + (t + 1) * BK;
+#pragma unroll
+        for (int i = 0; i < EA; i++) ra[i] = la.load(sa[i], kt);
+#pragma unroll
+        for (int i = 0; i < EB; i++) rb[i] = lb.load(sb[i], kt);
+      }
+      compute_tile(buf);
+      if (more) {
+        T* a1 = &As[buf ^ 1][0][0];
+        T* b1 = &Bs[buf ^ 1][0][0];
+#pragma unroll
+        for (int i = 0; i < EA; i++) a1[oa[i]] = ra[i];
+#pragma unroll
+        for (int i = 0; i < EB; i++) b1[ob[i]] = rb[i];
+      }
+      __syncthreads();
+    }
   }
 
   if constexpr (kTwoLevel) {

@@ -294,13 +294,13 @@ static int launch_by_rows(cudaStream_t st, const LA& la, const LB& lb, const Epi
   return launch<T, typename ConvCfgs<T>::C128>(st, la, lb, epi, M, N, K, 1, K);
 }
 
-// conv_direct.cu: shared-memory-staged direct kernels (fast path); *done == false -> use the gather kernels here
-template <class T>
-int conv2d_forward_direct(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const T* input,
-                          const T* kernel, const T* bias, T* output, bool* done);
-template <class T>
-int conv2d_dgrad_direct(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const T* grad_output,
-                        const T* kernel, T* grad_input, bool* done);
+// conv_direct.cu: float32 shared-memory-staged direct kernels (fast path); *done == false -> use the gather kernels
+int conv2d_forward_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                              const float* kernel, const float* bias, float* output, bool* done);
+int conv2d_dgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
+                            const float* kernel, float* grad_input, bool* done);
+int conv2d_wgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                            const float* grad_output, float** part_out, int* groups_out, bool* done);
 std::atomic<int> g_conv_path{AM_CONV_AUTO};
 static bool direct_enabled() { return g_conv_path.load() == AM_CONV_AUTO; }
 
@@ -311,10 +311,12 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   if (!make_geom(d, &g)) { set_last_error("conv2d_forward: invalid geometry"); return AM_ERR_INVALID; }
   if (g.Nimg == 0) return AM_OK;
   if (!input || !kernel || !output) { set_last_error("conv2d_forward: null pointer"); return AM_ERR_INVALID; }
-  if (direct_enabled()) {
-    bool done = false;
-    int rcd = conv2d_forward_direct<T>(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
-    if (rcd || done) return rcd;
+  if constexpr (std::is_same<T, float>::value) {
+    if (direct_enabled()) {
+      bool done = false;
+      int rcd = conv2d_forward_direct_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
+      if (rcd || done) return rcd;
+    }
   }
   int2 *tabF, *tabD, *tabW;
   int rc = get_tables(st, d, g, &tabF, &tabD, &tabW);
@@ -343,9 +345,11 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
   if (rc) return rc;
 
   bool dgrad_done = false;
-  if (grad_input && g.Nimg > 0 && direct_enabled()) {
-    rc = conv2d_dgrad_direct<T>(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
-    if (rc) return rc;
+  if constexpr (std::is_same<T, float>::value) {
+    if (grad_input && g.Nimg > 0 && direct_enabled()) {
+      rc = conv2d_dgrad_direct_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      if (rc) return rc;
+    }
   }
   if (grad_input && g.Nimg > 0 && !dgrad_done) {          // dgrad, gather form (any stride)
     WeightTLoader<T> la{kernel, tabW, g, KD};
@@ -356,6 +360,21 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
     if (rc) return rc;
   }
 
+  if constexpr (std::is_same<T, float>::value) {
+    if ((grad_kernel || grad_bias) && direct_enabled() && g.Nimg > 0) {
+      float* part = nullptr; int groups = 0; bool done = false;
+      rc = conv2d_wgrad_direct_f32(st, d, g.Ho, g.Wo, input, grad_output, &part, &groups, &done);
+      if (rc) return rc;
+      if (done) {
+        const int64_t Nv = g.Kc + 1, total = g.Cout * Nv;
+        wgrad_reduce_kernel<float><<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(part, groups, g.Cout, g.Kc, Nv,
+                                                                                  grad_kernel, grad_bias);
+        g_launch_count++;
+        AM_CUDA_TRY(cudaGetLastError());
+        return AM_OK;
+      }
+    }
+  }
   if (grad_kernel || grad_bias) {          // wgrad (+ grad_bias as a ones-column), split over the batch
     const int64_t Nv = g.Kc + 1;
     const bool small = g.Cout <= 32 && Nv <= 64;

@@ -79,9 +79,11 @@ def conv2d(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None 
 
 
 def conv2d_backward(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None,
-                    padding, strides, dilation, grad_output: torch.Tensor):
+                    padding, strides, dilation, grad_output: torch.Tensor,
+                    need_input_grad: bool = True, need_kernel_grad: bool = True):
     """Returns (grad_input, grad_kernel, grad_bias); grad_bias has bias' shape ([Cout,1,1]) or is
-    None when there is no bias (nnp_convolution.nim:91-94)."""
+    None when there is no bias (nnp_convolution.nim:91-94).  `need_*_grad=False` skips that gradient
+    (returned as None) — the C ABI takes NULL for any output it should not compute."""
     d = _desc(input, kernel, padding, strides, dilation)
     if bias is not None and bias.numel() == 0:
         bias = None
@@ -89,11 +91,13 @@ def conv2d_backward(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tenso
     want = conv_out_dims(input.shape, kernel.shape, padding, strides, dilation)
     if tuple(grad_output.shape) != tuple(want):
         raise IndexError(f"conv2d_backward: grad_output shape {tuple(grad_output.shape)} != {want}")
-    gin = torch.empty_like(input)
-    gk = torch.empty_like(kernel)
-    gb = torch.empty((kernel.shape[0], 1, 1), dtype=input.dtype, device=input.device) if bias is not None else None
+    gin = torch.empty_like(input) if need_input_grad else None
+    gk = torch.empty_like(kernel) if need_kernel_grad else None
+    gb = (torch.empty((kernel.shape[0], 1, 1), dtype=input.dtype, device=input.device)
+          if (bias is not None and need_kernel_grad) else None)
     with torch.cuda.device(input.device):
         _capi.check(getattr(_capi.lib(), f"am_conv2d_backward_{suf}")(
             _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(), grad_output.data_ptr(),
-            gin.data_ptr(), gk.data_ptr(), gb.data_ptr() if gb is not None else None))
+            gin.data_ptr() if gin is not None else None, gk.data_ptr() if gk is not None else None,
+            gb.data_ptr() if gb is not None else None))
     return gin, gk, gb

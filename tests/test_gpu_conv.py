@@ -140,6 +140,19 @@ def test_no_bias_and_partial_gradients(am, oracle):
     assert rel(gi.cpu().numpy(), wgi) <= 1e-4 and rel(gw.cpu().numpy(), wgw) <= 1e-4
 
 
+def test_partial_gradients(am, oracle):
+    """need_input_grad / need_kernel_grad = False -> NULL pointers on the C ABI, that gradient is skipped."""
+    rng = np.random.default_rng(9)
+    x = rng.random((3, 4, 10, 10)).astype(np.float32); k = (rng.random((6, 4, 5, 5)) - 0.5).astype(np.float32)
+    b = rng.random((6, 1, 1)).astype(np.float32)
+    go = (rng.random((3, 6, 6, 6)) - 0.5).astype(np.float32)
+    wgi, wgw, wgb = oracle.conv2d_backward(x, k, go)
+    gi, gw, gb = am.conv2d_backward(dev(x), dev(k), dev(b), (0, 0), (1, 1), (1, 1), dev(go), need_kernel_grad=False)
+    assert gw is None and gb is None and rel(gi.cpu().numpy(), wgi) <= 1e-4
+    gi, gw, gb = am.conv2d_backward(dev(x), dev(k), dev(b), (0, 0), (1, 1), (1, 1), dev(go), need_input_grad=False)
+    assert gi is None and rel(gw.cpu().numpy(), wgw) <= 1e-4 and rel(gb.cpu().numpy(), wgb) <= 1e-4
+
+
 def test_errors(am):
     x = torch.zeros((1, 3, 8, 8), device="cuda"); k = torch.zeros((2, 4, 3, 3), device="cuda")
     with pytest.raises(IndexError):

@@ -110,7 +110,7 @@ def exp_tc2_f4(): return _tc_parity(2, 4)
 def exp_tc2_f8(): return _tc_parity(2, 8)
 
 
-def _gemm_speed(dt, n, path=None, reps=5):
+def _gemm_speed(dt, n, path=None, reps=5, wide=False):
     import torch
     import arraymancer_b200 as am
     if path is not None:
@@ -119,6 +119,9 @@ def _gemm_speed(dt, n, path=None, reps=5):
     if dt in ("f32", "f64"):
         A = torch.rand(n, n, device="cuda", dtype=tdt) * 2 - 1
         B = torch.rand(n, n, device="cuda", dtype=tdt) * 2 - 1
+    elif wide:
+        A = torch.randint(-2**62, 2**62, (n, n), device="cuda", dtype=tdt)
+        B = torch.randint(-2**62, 2**62, (n, n), device="cuda", dtype=tdt)
     else:
         A = torch.randint(0, 100, (n, n), device="cuda", dtype=tdt)
         B = torch.randint(0, 100, (n, n), device="cuda", dtype=tdt)
@@ -132,6 +135,10 @@ def exp_simt_speed():
     for dt, n in [("i64", 1500), ("i64", 4096), ("i32", 1500), ("i32", 4096), ("f64", 1500), ("f64", 4096),
                   ("f64", 8192), ("f32", 4096)]:
         res[f"{dt}_{n}"] = _gemm_speed(dt, n, path=1, reps=3)
+    for n in (1500, 4096, 8192):
+        res[f"i64_fullrange_{n}"] = _gemm_speed("i64", n, reps=3, wide=True)
+    res["i64_8192"] = _gemm_speed("i64", 8192, reps=3)
+    res["i32_8192"] = _gemm_speed("i32", 8192, reps=3)
     return res
 
 
@@ -158,6 +165,28 @@ def exp_f64_speed():
         for n in (1500, 4096, 8192):
             res[f"{name}_{n}"] = _gemm_speed("f64", n, reps=3)
     am.set_f64_path(am.F64_AUTO)
+    return res
+
+
+def exp_conv_sweep():
+    """tile-plan sweep of the direct conv kernels (env overrides read at plan time)"""
+    import torch
+    import arraymancer_b200 as am
+    res = {}
+    layers = [("cv1", (4096, 1, 28, 28), (20, 1, 5, 5)), ("cv2", (4096, 20, 12, 12), (50, 20, 5, 5))]
+    for name, xs, ks in layers:
+        X = torch.rand(xs, device="cuda"); K_ = torch.randn(ks, device="cuda") * 0.1; B_ = torch.zeros(ks[0], 1, 1, device="cuda")
+        out = am.conv2d(X, K_, B_); go = torch.ones_like(out)
+        for maxt in (128, 256, 384, 512):
+            for ct, px in ((4, 4), (4, 8), (8, 4), (8, 8)):
+                for kb in (24, 40, 80):
+                    os.environ.update(AM_CONV_MAXT=str(maxt), AM_CONV_CT=str(ct), AM_CONV_PX=str(px), AM_CONV_SMEMKB=str(kb))
+                    try:
+                        f, _ = _time_gpu(lambda: am.conv2d(X, K_, B_), warm=1, reps=3)
+                        d, _ = _time_gpu(lambda: am.conv2d_backward(X, K_, B_, (0, 0), (1, 1), (1, 1), go, need_kernel_grad=False), warm=1, reps=3)
+                        res[f"{name}_t{maxt}_ct{ct}_px{px}_kb{kb}"] = [round(f, 4), round(d, 4)]
+                    except Exception as e:  # noqa
+                        res[f"{name}_t{maxt}_ct{ct}_px{px}_kb{kb}"] = str(e)[:60]
     return res
 
 
@@ -205,8 +234,11 @@ def exp_conv_speed():
         go = torch.ones_like(out)
         med, best = _time_gpu(lambda: am.conv2d(X, K_, B_), reps=5)
         bmed, bbest = _time_gpu(lambda: am.conv2d_backward(X, K_, B_, (0, 0), (1, 1), (1, 1), go), reps=5)
+        dmed, _ = _time_gpu(lambda: am.conv2d_backward(X, K_, B_, (0, 0), (1, 1), (1, 1), go, need_kernel_grad=False), reps=5)
+        wmed, _ = _time_gpu(lambda: am.conv2d_backward(X, K_, B_, (0, 0), (1, 1), (1, 1), go, need_input_grad=False), reps=5)
         flops = 2 * out.numel() * ks[1] * ks[2] * ks[3]
-        res[name] = {"fwd_ms": med, "fwd_gflops": flops / med / 1e6, "bwd_ms": bmed, "bwd_gflops": 2 * flops / bmed / 1e6}
+        res[name] = {"fwd_ms": med, "fwd_gflops": flops / med / 1e6, "bwd_ms": bmed, "bwd_gflops": 2 * flops / bmed / 1e6,
+                     "dgrad_ms": dmed, "wgrad_ms": wmed}
     return res
 
 

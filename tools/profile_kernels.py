@@ -32,6 +32,13 @@ if what in ("simt", "all"):
     gemm(torch.int32, 4096)
     gemm(torch.float32, 4096, am.F32_SIMT)
     gemm(torch.int64, 1500)
+if what == "i64wide":
+    n = 4096
+    A = torch.randint(-2**62, 2**62, (n, n), device="cuda", dtype=torch.int64); B = torch.randint(-2**62, 2**62, (n, n), device="cuda", dtype=torch.int64)
+    C = torch.empty(n, n, device="cuda", dtype=torch.int64)
+    for _ in range(reps):
+        am.gemm_strided(1, A, B, 0, C)
+    torch.cuda.synchronize()
 if what in ("tc", "all"):
     gemm(torch.float32, 8192, am.F32_TC)
 if what in ("conv", "all"):

@@ -361,3 +361,15 @@ def test_prepacked_operands(am, oracle):
     am.gemm_packed(1.0, pa, pb, 0.0, C)
     assert rel_fro(C.cpu().numpy(), oracle.matmul(a2, b)) <= F32_TOL
     pa.free(); pb.free()
+
+
+def test_cpp_host_mirror_known_answers():
+    """The C++ host-side mirror (arraymancer_b200/host/arraymancer_b200.hpp) — CudaTensor, cuda(), `*`, gemm, conv2d,
+    conv2d_backward over the C ABI — replays the reference's CUDA test vectors (tests/cpp/test_host_mirror.cpp)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_host_mirror")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_host_mirror not built (run __graft_entry__.build())")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.startswith("OK"), p.stdout + p.stderr

@@ -109,7 +109,7 @@ def set_f64_path(path: int) -> None:
     check(lib().am_set_f64_path(path))
 
 
-CONV_AUTO, CONV_GATHER = 0, 1
+CONV_AUTO, CONV_GATHER, CONV_DIRECT, CONV_TC = 0, 1, 2, 3
 
 
 def set_conv_path(path: int) -> None:

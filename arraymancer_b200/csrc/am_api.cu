@@ -322,7 +322,7 @@ DEF_CUBLAS(f32, float)
 DEF_CUBLAS(f64, double)
 
 int am_set_conv_path(int path) {
-  if (path != AM_CONV_AUTO && path != AM_CONV_GATHER) { set_last_error("am_set_conv_path: bad selector"); return AM_ERR_INVALID; }
+  if (path < AM_CONV_AUTO || path > AM_CONV_TC) { set_last_error("am_set_conv_path: bad selector"); return AM_ERR_INVALID; }
   am::g_conv_path.store(path);
   return AM_OK;
 }

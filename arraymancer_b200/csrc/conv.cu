@@ -301,8 +301,14 @@ int conv2d_dgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho
                             const float* kernel, float* grad_input, bool* done);
 int conv2d_wgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
                             const float* grad_output, float** part_out, int* groups_out, bool* done);
+// conv_tc.cu: tcgen05 implicit-GEMM kernels (float32, Cout <= 64); *done == false -> next path
+int conv2d_forward_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                          const float* kernel, const float* bias, float* output, bool* done);
+int conv2d_dgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
+                        const float* kernel, float* grad_input, bool* done);
 std::atomic<int> g_conv_path{AM_CONV_AUTO};
-static bool direct_enabled() { return g_conv_path.load() == AM_CONV_AUTO; }
+static bool direct_enabled() { return g_conv_path.load() != AM_CONV_GATHER; }
+static bool tc_enabled() { return g_conv_path.load() == AM_CONV_TC; }
 
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
@@ -312,6 +318,11 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   if (g.Nimg == 0) return AM_OK;
   if (!input || !kernel || !output) { set_last_error("conv2d_forward: null pointer"); return AM_ERR_INVALID; }
   if constexpr (std::is_same<T, float>::value) {
+    if (tc_enabled()) {
+      bool done = false;
+      int rcd = conv2d_forward_tc_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
+      if (rcd || done) return rcd;
+    }
     if (direct_enabled()) {
       bool done = false;
       int rcd = conv2d_forward_direct_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
@@ -346,7 +357,11 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
 
   bool dgrad_done = false;
   if constexpr (std::is_same<T, float>::value) {
-    if (grad_input && g.Nimg > 0 && direct_enabled()) {
+    if (grad_input && g.Nimg > 0 && tc_enabled()) {
+      rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      if (rc) return rc;
+    }
+    if (grad_input && g.Nimg > 0 && !dgrad_done && direct_enabled()) {
       rc = conv2d_dgrad_direct_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
       if (rc) return rc;
     }

@@ -100,6 +100,7 @@ struct TcArgs {
   int kblocks;             // Kpad / 32
   int flush_kb;            // k-blocks per tensor-core accumulation chain
   int tiles_m, tiles_n;
+  int group;               // M-tiles per rasterisation group
   float* C; int64_t rsC, csC;
   float alpha, beta;
 };
@@ -130,13 +131,24 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
 
   // tile of this CTA (pair): grouped rasterisation, 8 M-tiles per group, for L2 reuse of the B panels
   const int tile = (int)(blockIdx.x / CG);
-  constexpr int GROUP = 8;
-  const int group_size = GROUP * p.tiles_n;
-  const int g = tile / group_size;
-  const int first_m = g * GROUP;
-  const int gm = (p.tiles_m - first_m < GROUP) ? (p.tiles_m - first_m) : GROUP;
-  const int tm = first_m + (tile % group_size) % gm;
-  const int tn = (tile % group_size) / gm;
+  int tm, tn;
+  if (p.group > 0) {            // groups of `group` M-tiles, M fastest inside a group
+    const int GROUP = p.group;
+    const int group_size = GROUP * p.tiles_n;
+    const int g = tile / group_size;
+    const int first_m = g * GROUP;
+    const int gm = (p.tiles_m - first_m < GROUP) ? (p.tiles_m - first_m) : GROUP;
+    tm = first_m + (tile % group_size) % gm;
+    tn = (tile % group_size) / gm;
+  } else {                      // groups of `-group` N-tiles, N fastest inside a group
+    const int GROUP = -p.group;
+    const int group_size = GROUP * p.tiles_m;
+    const int g = tile / group_size;
+    const int first_n = g * GROUP;
+    const int gn = (p.tiles_n - first_n < GROUP) ? (p.tiles_n - first_n) : GROUP;
+    tn = first_n + (tile % group_size) % gn;
+    tm = (tile % group_size) / gn;
+  }
   const int row0 = tm * Cfg::TILE_M + (int)cta_rank * 128;     // first A row staged by this CTA
   const int col0 = tn * Cfg::TILE_N;                           // first B row (output column) of the tile
 
@@ -380,7 +392,9 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
       (rc = make_tmap(&tms[2], Q.hi, Q.Rpad, Q.Kpad, bk)) || (rc = make_tmap(&tms[3], Q.lo, Q.Rpad, Q.Kpad, bk)))
     return rc;
   TcArgs args;
-  args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env;
+  static int group_env = 0;    // 0 = not read yet; > 0: groups of M-tiles (M fastest), < 0: groups of N-tiles (N fastest)
+  if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 4; }
+  args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
   args.tiles_n = (int)ceil_div(Q.R, 256);
   if (cta_group == 2) {

@@ -9,13 +9,13 @@ namespace am {
 
 template <int CHAINS>
 __global__ void __launch_bounds__(256) i64_narrow_peak_kernel(int64_t* out, int iters, int64_t a0, int64_t b0) {
-  int64_t acc[CHAINS];
-  int64_t a = a0 + threadIdx.x, b = b0;
+  int64_t acc[CHAINS], bb[CHAINS];
+  int64_t a = a0 + threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < CHAINS; i++) acc[i] = i;
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i; bb[i] = b0 + 7 * i + (threadIdx.x & 3); }   // distinct per chain: products cannot be shared
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int i = 0; i < CHAINS; i++) acc[i] = mac_narrow_i64(a, b, acc[i]);
+    for (int i = 0; i < CHAINS; i++) acc[i] = mac_narrow_i64(a, bb[i], acc[i]);
     a = (int32_t)(a + acc[0]);
   }
   int64_t s = 0;
@@ -26,13 +26,20 @@ __global__ void __launch_bounds__(256) i64_narrow_peak_kernel(int64_t* out, int 
 
 template <class T, int CHAINS>
 __global__ void __launch_bounds__(256) simt_peak_kernel(T* out, int iters, T a0, T b0) {
-  T acc[CHAINS];
-  T a = a0 + (T)threadIdx.x, b = b0;
+  T acc[CHAINS], bb[CHAINS];
+  T a = a0 + (T)threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < CHAINS; i++) acc[i] = (T)i;
+  for (int i = 0; i < CHAINS; i++) {
+    acc[i] = (T)i;
+    // a distinct multiplicand per chain, like the b-fragment of a register tile: integer products / cross terms
+    // cannot be computed once and shared between chains (the first version of this benchmark allowed that and
+    // over-stated the int64 rate: 15.6 TOP/s "peak" vs 9.3 from the IMAD-slot count)
+    if constexpr (std::is_floating_point<T>::value) bb[i] = b0 + (T)(i * 0.001);
+    else bb[i] = (T)(b0 + (T)(0x10001 * i) + (T)(threadIdx.x & 3) + (sizeof(T) == 8 ? ((T)i << 33) : (T)0));
+  }
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int i = 0; i < CHAINS; i++) acc[i] = mac<T>(a, b, acc[i]);
+    for (int i = 0; i < CHAINS; i++) acc[i] = mac<T>(a, bb[i], acc[i]);
     a = (T)(a + acc[0]);       // keep the multiplicand live and data dependent (1 extra op / CHAINS macs)
   }
   T s = 0;
@@ -136,7 +143,7 @@ int microbench(int which, double* tops) {
   float ms = 0;
   const int blocks = sms * 8, threads = 256;
   double ops = 0;
-  constexpr int CH = 16;
+  constexpr int CH = 12;
   switch (which) {
     case 0: {
       const int iters = 1 << 15;

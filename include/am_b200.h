@@ -133,10 +133,15 @@ typedef struct am_conv2d_desc {
 } am_conv2d_desc;
 
 AM_API int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo);
-/* Conv kernel selector (process-wide, default AM_CONV_AUTO): AUTO = shared-memory-staged direct kernel for
- * forward and stride-1 data gradient when the tiles fit, generic gather kernel otherwise; GATHER forces the
- * generic implicit-GEMM gather kernels everywhere (fallback / comparison). */
-enum { AM_CONV_AUTO = 0, AM_CONV_GATHER = 1 };
+/* Conv kernel selector (process-wide, default AM_CONV_AUTO):
+ * AUTO   = float32: shared-memory-staged direct SIMT kernels (forward / stride-1 dgrad / wgrad, kW in {1,3,5,7},
+ *          dilation 1) when the tiles fit, generic gather kernels otherwise; other dtypes: generic gather kernels;
+ * GATHER = generic implicit-GEMM gather kernels everywhere (fallback / comparison);
+ * DIRECT = same as AUTO (kept for symmetry with the test matrix);
+ * TC     = float32 forward / stride-1 dgrad on the tcgen05 implicit-GEMM kernel (Cout <= 64) — correct and tested,
+ *          but its per-element global gather is latency-bound (measured slower than DIRECT on the LeNet layers,
+ *          profiles/r01_bringup.md), so it is opt-in. */
+enum { AM_CONV_AUTO = 0, AM_CONV_GATHER = 1, AM_CONV_DIRECT = 2, AM_CONV_TC = 3 };
 AM_API int am_set_conv_path(int path);
 
 #define AM_DECL_CONV(SUF, T)                                                                     \

@@ -95,11 +95,12 @@ CASES = [  # input, kernel, padding, stride, dilation
 ]
 
 
-@pytest.fixture(params=["auto", "gather"])
+@pytest.fixture(params=["auto", "tc", "gather"])
 def conv_path(request, am):
-    """Both kernel families: the smem-staged direct kernels (AUTO) and the generic gather kernels (fallback)."""
+    """All three kernel families: smem-staged direct SIMT kernels (AUTO), tcgen05 implicit GEMM (TC, opt-in) and the
+    generic gather kernels (GATHER, the fallback)."""
     from arraymancer_b200 import _capi
-    _capi.set_conv_path(_capi.CONV_GATHER if request.param == "gather" else _capi.CONV_AUTO)
+    _capi.set_conv_path({"auto": _capi.CONV_AUTO, "tc": _capi.CONV_TC, "gather": _capi.CONV_GATHER}[request.param])
     yield request.param
     _capi.set_conv_path(_capi.CONV_AUTO)
 

@@ -35,6 +35,7 @@ struct DirectArgs {
   int SEGS;                     // PX-wide segments per output row = ceil(WO / PX)
   int CO_B, CG, CI_B;           // output channels per CTA (padded), channel groups, input channels per block
   int bands;                    // ceil(HO / TH)
+  int64_t nunits;               // ceil(N / IMGS) * bands
 };
 
 template <int CT, int PX, int KW>
@@ -44,9 +45,13 @@ conv_direct_f32_kernel(const DirectArgs a) {
   float* w_s = reinterpret_cast<float*>(smem_raw);                 // [CI_B][kH][KW][CO_B], co contiguous
   float* in_s = w_s + (size_t)a.CI_B * a.kH * KW * a.CO_B;         // [IMGS][CI_B][IH_T][IW_S] (+ slack)
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int64_t n0 = (int64_t)(blockIdx.x / a.bands) * a.IMGS;
-  const int ho0 = (int)(blockIdx.x % a.bands) * a.TH;
   const int co0 = blockIdx.y * a.CO_B;
+  const bool single_block = a.CI_B >= a.C;             // weights then stay valid in smem across units
+  // PERSISTENT: a CTA walks (image group, row band) units strided over the grid — tiny CTAs were launch-bound
+  // (occupancy 30 % on LeNet cv1) and re-staged the weights every time
+  for (int64_t unit = blockIdx.x; unit < a.nunits; unit += gridDim.x) {
+  const int64_t n0 = (unit / a.bands) * a.IMGS;
+  const int ho0 = (int)(unit % a.bands) * a.TH;
   const int imgs = (int)((a.N - n0 < a.IMGS) ? a.N - n0 : a.IMGS);
   const int th = (a.HO - ho0 < a.TH) ? a.HO - ho0 : a.TH;
 
@@ -78,7 +83,7 @@ conv_direct_f32_kernel(const DirectArgs a) {
     const int cib = (a.C - cb < a.CI_B) ? a.C - cb : a.CI_B;
     __syncthreads();                                      // previous block fully consumed
     // ---- stage the weight slice from the packed copy: rows of CO_B contiguous floats, 128-bit coalesced
-    {
+    if (!(single_block && unit != (int64_t)blockIdx.x)) {
       const int rows = cib * a.kH * KW, vec_per_row = a.CO_B / 4;
       const float* wsrc = a.wp + (size_t)cb * a.kH * KW * a.CO_P + co0;
       for (int i = tid; i < rows * vec_per_row; i += nt) {
@@ -155,6 +160,7 @@ conv_direct_f32_kernel(const DirectArgs a) {
       }
     }
   }
+  }   // unit loop
 }
 
 // wp[k][c] = W(c, ci, kh, kw) for k = (ci*kH + kh)*KW + kw, c < CO_P (zero for c >= CO): one tiny pass per call,
@@ -244,8 +250,17 @@ static int launch_direct(cudaStream_t st, DirectArgs& a, int KW, bool* done) {
   int ct = 0, px = 0, nthreads = 0, grid_y = 0;
   size_t smem = 0;
   if (!plan_direct(a, KW, &ct, &px, &nthreads, &smem, &grid_y)) return AM_OK;
-  const int64_t gx = ceil_div(a.N, a.IMGS) * a.bands;
-  if (gx > 2147483647ll || grid_y > 65535) return AM_OK;
+  a.nunits = ceil_div(a.N, a.IMGS) * a.bands;
+  if (grid_y > 65535) return AM_OK;
+  // persistent grid: as many CTAs as can be resident (threads / shared memory), capped by the work
+  int per_sm = 2048 / nthreads;
+  const int by_smem = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > 16) per_sm = 16;
+  if (per_sm < 1) per_sm = 1;
+  int64_t gx = (int64_t)sm_count() * per_sm / grid_y;
+  if (gx < 1) gx = 1;
+  if (gx > a.nunits) gx = a.nunits;
   dim3 grid((unsigned)gx, (unsigned)grid_y);
   // pack the weights once (k-major, channel contiguous, padded to grid_y * CO_B channels)
   a.CO_P = grid_y * a.CO_B;

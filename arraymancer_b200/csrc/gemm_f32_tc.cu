@@ -101,10 +101,33 @@ struct TcArgs {
   int flush_kb;            // k-blocks per tensor-core accumulation chain
   int tiles_m, tiles_n;
   int group;               // M-tiles per rasterisation group
+  unsigned* sync_counter;  // grid barrier of the persistent schedule (zeroed before the launch); null = no barrier
   float* C; int64_t rsC, csC;
   float alpha, beta;
 };
 
+// tile index -> (tm, tn): groups of |group| tiles of one dimension, that dimension fastest inside a group, so that
+// any window of consecutive tile indices (= the tiles resident at the same time) is a compact 2-D block
+__device__ __forceinline__ void tile_coords(const TcArgs& p, int tile, int* tm, int* tn) {
+  if (p.group > 0) {
+    const int GROUP = p.group, group_size = GROUP * p.tiles_n, g = tile / group_size, first_m = g * GROUP;
+    const int gm = (p.tiles_m - first_m < GROUP) ? (p.tiles_m - first_m) : GROUP;
+    *tm = first_m + (tile % group_size) % gm;
+    *tn = (tile % group_size) / gm;
+  } else {
+    const int GROUP = -p.group, group_size = GROUP * p.tiles_m, g = tile / group_size, first_n = g * GROUP;
+    const int gn = (p.tiles_n - first_n < GROUP) ? (p.tiles_n - first_n) : GROUP;
+    *tn = first_n + (tile % group_size) % gn;
+    *tm = (tile % group_size) / gn;
+  }
+}
+
+// PERSISTENT kernel: one CTA (pair) per SM (pair), tiles strided over the clusters.  All pipelines (smem ring, TMEM
+// chain buffers) keep running across tile boundaries, so the epilogue of tile i overlaps the mainloop of tile i+1.
+// Before starting the loads of its next tile each producer passes a grid-wide barrier (global counter, bounded spin):
+// tiles of one wave then march through K in lockstep, which is what lets the 126 MB L2 capture the sharing of A/B
+// panels between co-resident tiles — without it the tiles drift apart over the waves and most panel reads go to
+// DRAM (measured 718-1221 GB per 32768^3 launch vs ~250 GB ideal; the extra DRAM power costs clocks under the cap).
 template <int CG>
 __global__ void __launch_bounds__(384, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
@@ -128,29 +151,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   const uint32_t lane = ptx::lane_id();
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-
-  // tile of this CTA (pair): grouped rasterisation, 8 M-tiles per group, for L2 reuse of the B panels
-  const int tile = (int)(blockIdx.x / CG);
-  int tm, tn;
-  if (p.group > 0) {            // groups of `group` M-tiles, M fastest inside a group
-    const int GROUP = p.group;
-    const int group_size = GROUP * p.tiles_n;
-    const int g = tile / group_size;
-    const int first_m = g * GROUP;
-    const int gm = (p.tiles_m - first_m < GROUP) ? (p.tiles_m - first_m) : GROUP;
-    tm = first_m + (tile % group_size) % gm;
-    tn = (tile % group_size) / gm;
-  } else {                      // groups of `-group` N-tiles, N fastest inside a group
-    const int GROUP = -p.group;
-    const int group_size = GROUP * p.tiles_m;
-    const int g = tile / group_size;
-    const int first_n = g * GROUP;
-    const int gn = (p.tiles_n - first_n < GROUP) ? (p.tiles_n - first_n) : GROUP;
-    tn = first_n + (tile % group_size) % gn;
-    tm = (tile % group_size) / gn;
-  }
-  const int row0 = tm * Cfg::TILE_M + (int)cta_rank * 128;     // first A row staged by this CTA
-  const int col0 = tn * Cfg::TILE_N;                           // first B row (output column) of the tile
+  const int cluster_id = (int)(blockIdx.x / CG), nclusters = (int)(gridDim.x / CG);
+  const int ntiles = p.tiles_m * p.tiles_n;
 
   if (CG == 2) ptx::cluster_sync();    // peer CTA must be resident before any remote barrier traffic
 
@@ -178,38 +180,58 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
 
   const int nkb = p.kblocks;
   const int flush = p.flush_kb;
-  const int nchains = (nkb + flush - 1) / flush;
+  const int nchains = (nkb + flush - 1) / flush;    // per tile
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ===================== TMA producer (one elected lane, in every CTA) =====================
       if (ptx::elect_one()) {
-        for (int kb = 0; kb < nkb; kb++) {
-          const int s = kb % Cfg::STAGES;
-          const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t sb = stage_base(s);
-          const int kc = kb * BK;
-          if constexpr (CG == 1) {
-            const uint32_t fb = full_bar(s);
-            ptx::mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-            ptx::tma_load_2d(sb + OFF_AHI, &tmAhi, fb, kc, row0);
-            ptx::tma_load_2d(sb + OFF_BHI, &tmBhi, fb, kc, col0);
-            ptx::tma_load_2d(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, col0 + 128);
-            ptx::tma_load_2d(sb + OFF_ALO, &tmAlo, fb, kc, row0);
-            ptx::tma_load_2d(sb + OFF_BLO, &tmBlo, fb, kc, col0);
-            ptx::tma_load_2d(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, col0 + 128);
-          } else {
-            // all transaction bytes of both CTAs land on the LEADER's full barrier
-            const uint32_t fb = ptx::mapa(full_bar(s), 0);
-            if (leader) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-            else ptx::mbar_arrive_cluster(fb);
-            const int b0 = col0 + (int)cta_rank * 128;     // this CTA supplies B rows [rank*128, +128) of the 256 columns
-            ptx::tma_load_2d_pair(sb + OFF_AHI, &tmAhi, fb, kc, row0);
-            ptx::tma_load_2d_pair(sb + OFF_BHI, &tmBhi, fb, kc, b0);
-            ptx::tma_load_2d_pair(sb + OFF_ALO, &tmAlo, fb, kc, row0);
-            ptx::tma_load_2d_pair(sb + OFF_BLO, &tmBlo, fb, kc, b0);
+        uint32_t it = 0;
+        unsigned long long expected = 0;      // cumulative arrivals the grid barrier must have seen
+        int round = 0;
+        for (int tile = cluster_id; tile < ntiles; tile += nclusters, round++) {
+          if (round > 0 && p.sync_counter != nullptr) {
+            // grid barrier (bounded spin): every CTA that has a tile in this round arrives once
+            const int rem = ntiles - round * nclusters;
+            expected += (unsigned long long)CG * (unsigned)(rem < nclusters ? rem : nclusters);
+            atomicAdd(p.sync_counter, 1u);
+            const long long t0 = clock64();
+            while (*((volatile unsigned*)p.sync_counter) < (unsigned)expected) {
+              if (clock64() - t0 > 400000) break;           // ~0.2 ms: never deadlock if a CTA is not co-resident
+              __nanosleep(64);
+            }
+          }
+          int tm, tn;
+          tile_coords(p, tile, &tm, &tn);
+          const int row0 = tm * Cfg::TILE_M + (int)cta_rank * 128;     // first A row staged by this CTA
+          const int col0 = tn * Cfg::TILE_N;                           // first B row (output column) of the tile
+          for (int kb = 0; kb < nkb; kb++, it++) {
+            const int s = it % Cfg::STAGES;
+            const uint32_t ph = (it / Cfg::STAGES) & 1u;
+            ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t sb = stage_base(s);
+            const int kc = kb * BK;
+            if constexpr (CG == 1) {
+              const uint32_t fb = full_bar(s);
+              ptx::mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+              ptx::tma_load_2d(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+              ptx::tma_load_2d(sb + OFF_BHI, &tmBhi, fb, kc, col0);
+              ptx::tma_load_2d(sb + OFF_BHI + Cfg::BOX_BYTES, &tmBhi, fb, kc, col0 + 128);
+              ptx::tma_load_2d(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+              ptx::tma_load_2d(sb + OFF_BLO, &tmBlo, fb, kc, col0);
+              ptx::tma_load_2d(sb + OFF_BLO + Cfg::BOX_BYTES, &tmBlo, fb, kc, col0 + 128);
+            } else {
+              // all transaction bytes of both CTAs land on the LEADER's full barrier
+              const uint32_t fb = ptx::mapa(full_bar(s), 0);
+              if (leader) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+              else ptx::mbar_arrive_cluster(fb);
+              const int b0 = col0 + (int)cta_rank * 128;     // this CTA supplies B rows [rank*128, +128) of the 256 columns
+              ptx::tma_load_2d_pair(sb + OFF_AHI, &tmAhi, fb, kc, row0);
+              ptx::tma_load_2d_pair(sb + OFF_BHI, &tmBhi, fb, kc, b0);
+              ptx::tma_load_2d_pair(sb + OFF_ALO, &tmAlo, fb, kc, row0);
+              ptx::tma_load_2d_pair(sb + OFF_BLO, &tmBlo, fb, kc, b0);
+            }
           }
         }
       }
@@ -218,34 +240,37 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       if (leader && ptx::elect_one()) {
         const uint64_t dhi = ptx::umma_desc_hi(Cfg::SBO, Cfg::ROW_BYTES);
         const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
-        int kb = 0;
-        for (int c = 0; c < nchains; c++) {
-          const int buf = c & 1;
-          ptx::mbar_wait(tempty_bar(buf), (((uint32_t)c >> 1) & 1u) ^ 1u);    // accumulate warps drained this buffer
-          ptx::tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)buf * 256u;
-          const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
-          for (bool first = true; kb < kb_end; kb++) {
-            const int s = kb % Cfg::STAGES;
-            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-            ptx::mbar_wait(full_bar(s), ph);
+        uint32_t it = 0, chain = 0;
+        for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+          int kb = 0;
+          for (int c = 0; c < nchains; c++, chain++) {
+            const int buf = chain & 1;
+            ptx::mbar_wait(tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);    // accumulate warps drained this buffer
             ptx::tc_fence_after();
-            const uint32_t sb = stage_base(s);
+            const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+            const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
+            for (bool first = true; kb < kb_end; kb++, it++) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1u;
+              ptx::mbar_wait(full_bar(s), ph);
+              ptx::tc_fence_after();
+              const uint32_t sb = stage_base(s);
 #pragma unroll
-            for (int k8 = 0; k8 < BK / 8; k8++) {
-              const uint32_t koff = k8 * 32;                       // 8 tf32 = 32 bytes along K inside the swizzle atom
-              const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff);
-              const uint64_t a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
-              const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff);
-              const uint64_t b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
-              ptx::umma_tf32<CG>(d, a_lo, b_hi, idesc, first ? 0u : 1u);   // small terms first
-              ptx::umma_tf32<CG>(d, a_hi, b_lo, idesc, 1u);
-              ptx::umma_tf32<CG>(d, a_hi, b_hi, idesc, 1u);
-              first = false;
+              for (int k8 = 0; k8 < BK / 8; k8++) {
+                const uint32_t koff = k8 * 32;                       // 8 tf32 = 32 bytes along K inside the swizzle atom
+                const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff);
+                const uint64_t a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
+                const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff);
+                const uint64_t b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
+                ptx::umma_tf32<CG>(d, a_lo, b_hi, idesc, first ? 0u : 1u);   // small terms first
+                ptx::umma_tf32<CG>(d, a_hi, b_lo, idesc, 1u);
+                ptx::umma_tf32<CG>(d, a_hi, b_hi, idesc, 1u);
+                first = false;
+              }
+              ptx::umma_commit<CG>(empty_bar(s));                    // frees the stage in both CTAs once the MMAs retire
             }
-            ptx::umma_commit<CG>(empty_bar(s));                    // frees the stage in both CTAs once the MMAs retire
+            ptx::umma_commit<CG>(tfull_bar(buf));                    // chain complete -> accumulate warps
           }
-          ptx::umma_commit<CG>(tfull_bar(buf));                    // chain complete -> accumulate warps
         }
       }
     }
@@ -254,42 +279,48 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;              // which 128 of the 256 columns
-    float acc[128];
-#pragma unroll
-    for (int i = 0; i < 128; i++) acc[i] = 0.f;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 128u;
     const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
-    for (int c = 0; c < nchains; c++) {
-      const int buf = c & 1;
-      ptx::mbar_wait(tfull_bar(buf), ((uint32_t)c >> 1) & 1u);
-      ptx::tc_fence_after();
+    uint32_t chain = 0;
+    for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+      float acc[128];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tlane + (uint32_t)buf * 256u + (uint32_t)j * 32u, r);
-        ptx::tmem_ld_wait();
+      for (int i = 0; i < 128; i++) acc[i] = 0.f;
+      for (int c = 0; c < nchains; c++, chain++) {
+        const int buf = chain & 1;
+        ptx::mbar_wait(tfull_bar(buf), (chain >> 1) & 1u);
+        ptx::tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(r[i]));
+        for (int j = 0; j < 4; j++) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tlane + (uint32_t)buf * 256u + (uint32_t)j * 32u, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(r[i]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * buf);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * buf);
-        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
-      }
-    }
-    // ---- epilogue: alpha/beta, strided stores (lanes run along C's unit-stride dimension)
-    const int64_t m = (int64_t)row0 + q * 32 + (int)lane;
-    if (m < p.M) {
-      float* crow = p.C + m * p.rsC;
-      const float alpha = p.alpha, beta = p.beta;
+      // ---- epilogue: alpha/beta, strided stores (lanes run along C's unit-stride dimension); overlaps the next tile
+      int tm, tn;
+      tile_coords(p, tile, &tm, &tn);
+      const int64_t m = (int64_t)tm * Cfg::TILE_M + (int64_t)cta_rank * 128 + q * 32 + (int)lane;
+      const int64_t col0 = (int64_t)tn * Cfg::TILE_N;
+      if (m < p.M) {
+        float* crow = p.C + m * p.rsC;
+        const float alpha = p.alpha, beta = p.beta;
 #pragma unroll
-      for (int i = 0; i < 128; i++) {
-        const int64_t n = (int64_t)col0 + half * 128 + i;
-        if (n < p.N) {
-          float* pc = crow + n * p.csC;
-          const float cold = (beta != 0.f) ? *pc : 0.f;
-          *pc = epilogue_value<float>(alpha, acc[i], beta, cold);
+        for (int i = 0; i < 128; i++) {
+          const int64_t n = col0 + half * 128 + i;
+          if (n < p.N) {
+            float* pc = crow + n * p.csC;
+            const float cold = (beta != 0.f) ? *pc : 0.f;
+            *pc = epilogue_value<float>(alpha, acc[i], beta, cold);
+          }
         }
       }
     }
@@ -346,7 +377,10 @@ static int launch_tc(cudaStream_t st, const CUtensorMap* tms, const TcArgs& args
   auto kern = gemm_tf32x3_kernel<CG>;
   AM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(args.tiles_m * args.tiles_n * CG), 1, 1);
+  const int ntiles = args.tiles_m * args.tiles_n;
+  const int resident = sm_count() / CG;                          // one CTA (pair) per SM (pair)
+  const int nclusters = ntiles < resident ? ntiles : resident;
+  cfg.gridDim = dim3((unsigned)(nclusters * CG), 1, 1);
   cfg.blockDim = dim3(Cfg::NTHREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
@@ -393,9 +427,21 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
     return rc;
   TcArgs args;
   static int group_env = 0;    // 0 = not read yet; > 0: groups of M-tiles (M fastest), < 0: groups of N-tiles (N fastest)
-  if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 4; }
+  if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 8; }
   args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
+  // grid-barrier counter of the persistent schedule: one slot of a small ring, zeroed in stream order
+  static int sync_env = -1;
+  if (sync_env < 0) { const char* e = getenv("AM_TC_SYNC"); sync_env = (e && e[0] == '0') ? 0 : 1; }
+  args.sync_counter = nullptr;
+  if (sync_env) {
+    static std::atomic<unsigned> ring{0};
+    void* base = nullptr;
+    if ((rc = workspace(kWsMisc, 64 * sizeof(int) + 1024, &base))) return rc;
+    unsigned* ctr = (unsigned*)base + 64 + (ring++ % 64);
+    AM_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
+    args.sync_counter = ctr;
+  }
   args.tiles_n = (int)ceil_div(Q.R, 256);
   if (cta_group == 2) {
     args.tiles_m = (int)ceil_div(P.R, 256);

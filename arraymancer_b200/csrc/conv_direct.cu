@@ -35,7 +35,7 @@ struct DirectArgs {
   int SEGS;                     // PX-wide segments per output row = ceil(WO / PX)
   int CO_B, CG, CI_B;           // output channels per CTA (padded), channel groups, input channels per block
   int bands;                    // ceil(HO / TH)
-  int64_t nunits;               // ceil(N / IMGS) * bands
+  int BUF_FLOATS;               // floats per half of the double-buffered stage (multiple of 4)
 };
 
 template <int CT, int PX, int KW>
@@ -43,15 +43,11 @@ __global__ void __launch_bounds__(512)
 conv_direct_f32_kernel(const DirectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* w_s = reinterpret_cast<float*>(smem_raw);                 // [CI_B][kH][KW][CO_B], co contiguous
-  float* in_s = w_s + (size_t)a.CI_B * a.kH * KW * a.CO_B;         // [IMGS][CI_B][IH_T][IW_S] (+ slack)
+  // two halves of [ weights [CI_B][kH][KW][CO_B] | inputs [IMGS][CI_B][IH_T][IW_S] ] (+ slack)
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t n0 = (int64_t)(blockIdx.x / a.bands) * a.IMGS;
+  const int ho0 = (int)(blockIdx.x % a.bands) * a.TH;
   const int co0 = blockIdx.y * a.CO_B;
-  const bool single_block = a.CI_B >= a.C;             // weights then stay valid in smem across units
-  // PERSISTENT: a CTA walks (image group, row band) units strided over the grid — tiny CTAs were launch-bound
-  // (occupancy 30 % on LeNet cv1) and re-staged the weights every time
-  for (int64_t unit = blockIdx.x; unit < a.nunits; unit += gridDim.x) {
-  const int64_t n0 = (unit / a.bands) * a.IMGS;
-  const int ho0 = (int)(unit % a.bands) * a.TH;
   const int imgs = (int)((a.N - n0 < a.IMGS) ? a.N - n0 : a.IMGS);
   const int th = (a.HO - ho0 < a.TH) ? a.HO - ho0 : a.TH;
 
@@ -79,40 +75,55 @@ conv_direct_f32_kernel(const DirectArgs a) {
   const int rows_per_iter = 32 / cols_per_iter;
   const int lane_row = lane / cols_per_iter, lane_col = lane - lane_row * cols_per_iter;
   const bool lane_ok = lane_row < rows_per_iter;
-  for (int cb = 0; cb < a.C; cb += a.CI_B) {
+  // Double-buffered staging with cp.async (LDGSTS): while the FMAs consume channel block cb from one half of the
+  // shared buffer, block cb+1 streams into the other half (zero-fill = padding) — one barrier per block instead of
+  // two, and the staging latency hides under compute (ncu: CTA-barrier stalls were 18-53 % on the first version).
+  const int buf_floats = a.BUF_FLOATS;                     // floats per buffer half (weights + inputs of one block)
+  const uint32_t smem_u32base = (uint32_t)__cvta_generic_to_shared(w_s);
+  auto issue_block = [&](int cb, int half) {
     const int cib = (a.C - cb < a.CI_B) ? a.C - cb : a.CI_B;
-    __syncthreads();                                      // previous block fully consumed
-    // ---- stage the weight slice from the packed copy: rows of CO_B contiguous floats, 128-bit coalesced
-    if (!(single_block && unit != (int64_t)blockIdx.x)) {
-      const int rows = cib * a.kH * KW, vec_per_row = a.CO_B / 4;
-      const float* wsrc = a.wp + (size_t)cb * a.kH * KW * a.CO_P + co0;
-      for (int i = tid; i < rows * vec_per_row; i += nt) {
-        const int k = i / vec_per_row, v = i - k * vec_per_row;
-        reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(wsrc + (size_t)k * a.CO_P)[v];
-      }
+    const uint32_t wdst = smem_u32base + (uint32_t)(half * buf_floats) * 4u;
+    const uint32_t xdst = wdst + (uint32_t)(a.CI_B * wk_elems) * 4u;
+    // weight slice from the packed copy: rows of CO_B contiguous floats, 16-byte cp.async
+    const int rows = cib * a.kH * KW, vec_per_row = a.CO_B / 4;
+    const float* wsrc = a.wp + (size_t)cb * a.kH * KW * a.CO_P + co0;
+    for (int i = tid; i < rows * vec_per_row; i += nt) {
+      const int k = i / vec_per_row, v = i - k * vec_per_row;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + 16u * (uint32_t)i), "l"(wsrc + (size_t)k * a.CO_P + 4 * v) : "memory");
     }
-    // ---- stage the input region of this channel block (zero outside the image = padding):
-    //      one warp per (image, channel) plane, lanes over (rows_per_iter x IW_S) pixels — no per-element division
+    // input region: one warp per (image, channel) plane, lanes over (rows_per_iter x IW_S) pixels, 4-byte cp.async
+    // with zero fill outside the image — no per-element division
     for (int pl = warp; pl < imgs * cib; pl += nwarps) {
       const int im = pl / cib, c = pl - im * cib;
       const float* src = a.x + ((n0 + im) * a.C + cb + c) * (int64_t)a.H * a.W;
-      float* dst = in_s + im * img_stride + c * ch_stride;
+      const uint32_t dst = xdst + (uint32_t)(im * img_stride + c * ch_stride) * 4u;
       if (lane_ok) {
         for (int ih = lane_row; ih < a.IH_T; ih += rows_per_iter) {
           for (int iw = lane_col; iw < a.IW_S; iw += cols_per_iter) {
             const int h = h_base + ih, w = iw - a.padW;
-            float v = 0.f;
-            if ((unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W) v = src[h * a.W + w];
-            dst[ih * a.IW_S + iw] = v;
+            const bool ok = (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W;
+            const float* sp = ok ? src + h * a.W + w : a.x;
+            const int nbytes = ok ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)(ih * a.IW_S + iw) * 4u), "l"(sp), "r"(nbytes) : "memory");
           }
         }
       }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_block(0, 0);
+  int half = 0;
+  for (int cb = 0; cb < a.C; cb += a.CI_B, half ^= 1) {
+    const int cib = (a.C - cb < a.CI_B) ? a.C - cb : a.CI_B;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                      // block cb landed; everyone is done with the other half
+    if (cb + a.CI_B < a.C) issue_block(cb + a.CI_B, half ^ 1);
+    const float* w_cur = w_s + half * buf_floats;
+    const float* in_cur = w_cur + a.CI_B * wk_elems;
     if (active) {
       for (int ci = 0; ci < cib; ci++) {
-        const float* xr = in_s + xbase + ci * ch_stride;
-        const float* wr = w_s + ci * wk_elems + cg * CT;
+        const float* xr = in_cur + xbase + ci * ch_stride;
+        const float* wr = w_cur + ci * wk_elems + cg * CT;
         for (int kh = 0; kh < a.kH; kh++) {
           // PX + KW - 1 consecutive inputs of tap row kh, as 128-bit loads (xbase and IW_S are multiples of 4)
           constexpr int NX = (PX + KW - 1 + 3) / 4;
@@ -160,7 +171,6 @@ conv_direct_f32_kernel(const DirectArgs a) {
       }
     }
   }
-  }   // unit loop
 }
 
 // wp[k][c] = W(c, ci, kh, kw) for k = (ci*kH + kh)*KW + kw, c < CO_P (zero for c >= CO): one tiny pass per call,
@@ -211,9 +221,9 @@ static bool plan_direct(DirectArgs& a, int KW, int* ct_out, int* px_out, int* nt
   const int IH_T = (TH - 1) + (a.kH - 1) + 1;
   // input-channel block: keep weights + inputs of a block under ~40 KB so several CTAs share an SM
   const size_t per_ci = ((size_t)a.kH * KW * CO_B + (size_t)IMGS * IH_T * IW_S) * sizeof(float);
-  int CI_B = (int)(((size_t)envi("AM_CONV_SMEMKB", 40) * 1024) / per_ci);
+  int CI_B = (int)(((size_t)envi("AM_CONV_SMEMKB", 24) * 1024) / per_ci);    // per half of the double buffer
   if (CI_B < 1) {
-    if (per_ci > 160 * 1024) return false;
+    if (per_ci > 100 * 1024) return false;          // two halves must fit the 227 KB of an SM
     CI_B = 1;
   }
   if (CI_B > a.C) CI_B = a.C;
@@ -223,7 +233,8 @@ static bool plan_direct(DirectArgs& a, int KW, int* ct_out, int* px_out, int* nt
   const int segs_cta = IMGS * TH * SEGS;
   *nthreads = padded(segs_cta * CG, 32);
   if (*nthreads > 512) return false;
-  *smem = (size_t)CI_B * per_ci + 64;                     // + slack: the last window may read a few floats past the tile
+  a.BUF_FLOATS = (int)padded((int)(((size_t)CI_B * per_ci) / sizeof(float)) + 16, 4);   // + slack: the last window may read a few floats past the tile
+  *smem = 2 * (size_t)a.BUF_FLOATS * sizeof(float);
   *grid_y = (a.CO + CO_B - 1) / CO_B;
   return true;
 }
@@ -250,17 +261,8 @@ static int launch_direct(cudaStream_t st, DirectArgs& a, int KW, bool* done) {
   int ct = 0, px = 0, nthreads = 0, grid_y = 0;
   size_t smem = 0;
   if (!plan_direct(a, KW, &ct, &px, &nthreads, &smem, &grid_y)) return AM_OK;
-  a.nunits = ceil_div(a.N, a.IMGS) * a.bands;
-  if (grid_y > 65535) return AM_OK;
-  // persistent grid: as many CTAs as can be resident (threads / shared memory), capped by the work
-  int per_sm = 2048 / nthreads;
-  const int by_smem = (int)((200 * 1024) / (smem + 1024));
-  if (per_sm > by_smem) per_sm = by_smem;
-  if (per_sm > 16) per_sm = 16;
-  if (per_sm < 1) per_sm = 1;
-  int64_t gx = (int64_t)sm_count() * per_sm / grid_y;
-  if (gx < 1) gx = 1;
-  if (gx > a.nunits) gx = a.nunits;
+  const int64_t gx = ceil_div(a.N, a.IMGS) * a.bands;
+  if (gx > 2147483647ll || grid_y > 65535) return AM_OK;
   dim3 grid((unsigned)gx, (unsigned)grid_y);
   // pack the weights once (k-major, channel contiguous, padded to grid_y * CO_B channels)
   a.CO_P = grid_y * a.CO_B;

@@ -221,7 +221,7 @@ static bool plan_direct(DirectArgs& a, int KW, int* ct_out, int* px_out, int* nt
   const int IH_T = (TH - 1) + (a.kH - 1) + 1;
   // input-channel block: keep weights + inputs of a block under ~40 KB so several CTAs share an SM
   const size_t per_ci = ((size_t)a.kH * KW * CO_B + (size_t)IMGS * IH_T * IW_S) * sizeof(float);
-  int CI_B = (int)(((size_t)envi("AM_CONV_SMEMKB", 24) * 1024) / per_ci);    // per half of the double buffer
+  int CI_B = (int)(((size_t)envi("AM_CONV_SMEMKB", 40) * 1024) / per_ci);    // per half of the double buffer
   if (CI_B < 1) {
     if (per_ci > 100 * 1024) return false;          // two halves must fit the 227 KB of an SM
     CI_B = 1;

@@ -306,6 +306,9 @@ int conv2d_forward_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, 
                           const float* kernel, const float* bias, float* output, bool* done);
 int conv2d_dgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
                         const float* kernel, float* grad_input, bool* done);
+// conv_tc_bwd.cu: data gradient as GEMM + col2im on the tensor cores (any stride / padding / dilation, Cout <= 64)
+int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
+                               const float* kernel, float* grad_input, bool* done);
 std::atomic<int> g_conv_path{AM_CONV_AUTO};
 static bool direct_enabled() { return g_conv_path.load() != AM_CONV_GATHER; }
 static bool tc_enabled() { return g_conv_path.load() == AM_CONV_TC; }
@@ -358,7 +361,9 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
   bool dgrad_done = false;
   if constexpr (std::is_same<T, float>::value) {
     if (grad_input && g.Nimg > 0 && tc_enabled()) {
-      rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      static const bool gather_form = getenv("AM_CONVTC_DGRAD_GATHER") != nullptr;      // older gather-form kernel (comparison)
+      if (gather_form) rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      else rc = conv2d_dgrad_col2im_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
       if (rc) return rc;
     }
     if (grad_input && g.Nimg > 0 && !dgrad_done && direct_enabled()) {

@@ -1,22 +1,26 @@
 // float32 conv2d forward / stride-1 data gradient as a fused implicit GEMM on the 5th-gen tensor cores
-// (tcgen05 kind::tf32, 3xTF32 split, fp32 accuracy).  The im2col matrix never exists in HBM *or* as a whole in
-// shared memory: per 32-wide k block the gather warps read the needed NCHW input pixels (L1/L2-cached, lanes along
-// consecutive output pixels), split them into tf32 hi/lo and write the 128-pixel x 32-k operand tile straight into
-// the 128B-swizzled K-major layout the UMMA descriptor expects; the weights (small) come pre-split via TMA.
+// (tcgen05 kind::tf32, 3xTF32 split, fp32 accuracy).  The im2col matrix never exists in HBM: the raw NCHW images a
+// tile of 128 output pixels needs are bulk-copied (TMA 1-D, cp.async.bulk) into shared memory once, and the gather
+// warps expand them from there, 32 k at a time, split into tf32 hi/lo, straight into TENSOR MEMORY (tcgen05.st): the
+// MMA reads its A operand from TMEM (lane = pixel, column = k), so the expansion costs no shared-memory bandwidth and
+// needs no swizzle; the weights (small, L2-resident) come pre-split via 2-D TMA into their own, deeper ring.
 //
 //   D[p, co] = sum_k im2col[p, k] * W[co, k],  M = 128 output pixels per tile (TMEM lanes), N = Cout (<= 64 per CTA),
 //   K = C*kH*kW.  GEMM view of conv.nim:81-106 (forward) and of col2im(W^T gout) (conv.nim:136-139, gather form).
 //
-// Persistent, warp-specialised CTA (384 threads), tiles strided over the grid:
-//   warp 0      TMA producer for the weight tiles (hi / lo planes, K-major, packed by conv_tc_pack_weights_kernel)
-//   warp 1      UMMA issuer: per 8-wide k step three tcgen05.mma (lo*hi, hi*lo, hi*hi), accumulation chains of
-//               `flush_kb` k blocks into one of two TMEM buffers (the tensor core truncates when it accumulates,
-//               see gemm_f32_tc.cu)
-//   warp 2      TMEM allocation
-//   warps 4-7   gather / split / swizzled-store of the im2col operand tile (thread r <-> output pixel r of the tile)
-//   warps 8-11  drain finished chains (tcgen05.ld) into register accumulators with round-to-nearest adds, then the
-//               epilogue: + bias, NCHW stores (lanes = consecutive pixels: coalesced)
+// Persistent, warp-specialised CTA, tiles strided over the grid:
+//   warp 0        TMA producer for the weight tiles (hi / lo planes, K-major, packed by conv_tc_pack_weights_kernel)
+//   warp 1        UMMA issuer: per 8-wide k step three tcgen05.mma (lo*hi, hi*lo, hi*hi), accumulation chains of
+//                 `flush_kb` k blocks into one of two TMEM buffers (the tensor core truncates when it accumulates,
+//                 see gemm_f32_tc.cu)
+//   warp 2        TMEM allocation
+//   warp 3        bulk-copy producer for the raw images of the NEXT tile (double-buffered)
+//   warps 4..19   `groups` (<= 4) gather groups of 128 threads (thread r <-> output pixel r <-> TMEM lane r); group g
+//                 expands the k blocks g, g + groups, ... so several of the 6 operand stages are being filled at once
+//   last 4 warps  drain finished chains (tcgen05.ld) into register accumulators with round-to-nearest adds, then the
+//                 epilogue: + bias, NCHW stores (lanes = consecutive pixels: coalesced)
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "am_common.cuh"
@@ -31,14 +35,19 @@ struct ConvTcArgs {
   float* y;             // [N][CO][HO][WO]     (grad_input for dgrad)
   const int2* tab;      // k -> {offset ci*H*W + kh*dH*W + kw*dW, (kh*dH << 16) | (kw*dW)}; Kpad entries
   int64_t P;            // total output pixels N*HO*WO
+  int64_t N;
   int C, H, W, CO, HO, WO, padH, padW, sH, sW;
   int K, kblocks;       // K' = C*kH*kW, ceil(K'/32)
   int NP;               // Cout padded to a multiple of 16 (<= 64): UMMA N and weight-tile rows
   int flush_kb;
   int ntiles;
+  int CHW;              // floats per input image
+  int stages;           // pipeline depth of the operand ring
+  int groups;           // gather groups (of 128 threads)
+  uint32_t raw_bytes;   // bytes of one raw-image buffer (max images a tile touches * CHW * 4, rounded up)
+  long long* dbg;       // optional: per-role wait-cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
 };
 
-constexpr int kCtStages = 4;
 constexpr int kCtABytes = 128 * 128;      // one plane of the im2col tile: 128 pixels x 32 floats
 
 __global__ void conv_tc_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
@@ -59,53 +68,82 @@ __global__ void conv_tc_pack_weights_kernel(const float* __restrict__ w, float* 
   }
 }
 
-__global__ void conv_tc_table_kernel(int2* tab, int K, int Kpad, int kH, int kW, int H, int W, int dH, int dW) {
+__global__ void conv_tc_table_kernel(int2* tab, int K, int Kpad, int kH, int kW, int H, int W, int dH, int dW, int checked) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Kpad; k += gridDim.x * blockDim.x) {
     if (k < K) {
       const int ci = k / (kH * kW), r = k - ci * (kH * kW), kh = r / kW, kw = r - kh * kW;
       tab[k] = make_int2(ci * H * W + kh * dH * W + kw * dW, ((kh * dH) << 16) | (kw * dW));
     } else {
-      tab[k] = make_int2(0, 0x7fff7fff);      // out-of-range taps: h0 + 32767 is never inside the image
+      // padded taps: the weights are zero; the checked variant also reads a zero (h0 + 32767 is never inside the image),
+      // the unchecked one re-reads tap 0 of the pixel's own window
+      tab[k] = make_int2(0, checked ? 0x7fff7fff : 0);
     }
   }
 }
 
-__global__ void __launch_bounds__(384, 1)
+// CHECK = the convolution has padding: taps outside the image read as zero (bounds test per element)
+constexpr int kCtAStages = 6;             // im2col operand stages in tensor memory: 64 columns each (hi 32 | lo 32)
+constexpr int kCtAccCols = 128;           // two accumulator buffers of up to 64 columns
+constexpr int kCtMaxBStages = 8;
+
+#define CT_TWAIT(counter, bar, ph) do { const long long t0_ = clock64(); ptx::mbar_wait(bar, ph); counter += clock64() - t0_; } while (0)
+
+template <bool CHECK>
+__global__ void __launch_bounds__(768, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int SB = a.stages;                                              // weight ring depth
   const uint32_t b_bytes = (uint32_t)a.NP * 128u;                     // one weight plane per stage
-  const uint32_t stage_bytes = 2u * kCtABytes + 2u * b_bytes;
+  const uint32_t stage_bytes = 2u * b_bytes;
   auto stage_base = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
-  const uint32_t OFF_AHI = 0, OFF_ALO = kCtABytes, OFF_BHI = 2 * kCtABytes, OFF_BLO = 2 * kCtABytes + b_bytes;
-  const uint32_t bar_base = smem_base + kCtStages * stage_bytes;
-  auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto full_b = [&](int s) { return bar_base + 8u * (kCtStages + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kCtStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * kCtStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * kCtStages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * kCtStages + 4);
-  const uint32_t tab_s = bar_base + 8u * (3 * kCtStages + 6);           // int2 tab[kblocks*32]
+  const uint32_t OFF_BHI = 0, OFF_BLO = b_bytes;
+  const uint32_t raw_base = smem_base + (uint32_t)SB * stage_bytes;     // two raw-image buffers
+  const uint32_t bar_base = raw_base + 2u * a.raw_bytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };               // 6
+  auto empty_a = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
+  auto full_b = [&](int s) { return bar_base + 8u * (12 + s); };        // 8
+  auto empty_b = [&](int s) { return bar_base + 8u * (20 + s); };       // 8
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (28 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (30 + b); };
+  auto raw_full = [&](int b) { return bar_base + 8u * (32 + b); };
+  auto raw_empty = [&](int b) { return bar_base + 8u * (34 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 36;
+  const uint32_t bias_s = bar_base + 8u * 38;                           // float bias[64] (zero when there is none)
+  const uint32_t tab_s = bias_s + 256u;                                 // int2 tab[kblocks*32]
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = ptx::lane_id();
   const int nkb = a.kblocks;
-  const uint32_t tmem_cols = (2u * (uint32_t)a.NP <= 32u) ? 32u : ((2u * a.NP <= 64u) ? 64u : 128u);
+  const int G = a.groups;
+  const int acc_warp0 = 20;                               // the last four of the 24 launched warps
+  const uint32_t tmem_cols = 512u;                        // accumulators (128) + 6 operand stages (384)
+  const int64_t HW = (int64_t)a.HO * a.WO;
 
   if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tensormap(&tmWhi); ptx::prefetch_tensormap(&tmWlo); }
   if (warp == 1 && ptx::elect_one()) {
-    for (int s = 0; s < kCtStages; s++) {
-      ptx::mbar_init(full_a(s), 128);      // every gather thread arrives after its swizzled stores
-      ptx::mbar_init(full_b(s), 1);        // TMA transaction bytes
-      ptx::mbar_init(empty_bar(s), 1);     // tcgen05.commit
+    for (int s = 0; s < kCtAStages; s++) {
+      ptx::mbar_init(full_a(s), 128);      // every thread of the filling group arrives after its tcgen05.st completed
+      ptx::mbar_init(empty_a(s), 1);       // tcgen05.commit
     }
-    for (int b = 0; b < 2; b++) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4); }
+    for (int s = 0; s < SB; s++) {
+      ptx::mbar_init(full_b(s), 1);        // TMA transaction bytes
+      ptx::mbar_init(empty_b(s), 1);       // tcgen05.commit
+    }
+    for (int b = 0; b < 2; b++) {
+      ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4);
+      ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, tmem_cols);
   for (int i = threadIdx.x; i < nkb * 32; i += blockDim.x) {            // k-decode table -> shared memory
     const int2 e = a.tab[i];
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab_s + 8u * i), "r"(e.x), "r"(e.y));
+  }
+  if (threadIdx.x < 64) {
+    const float bv = (a.bias != nullptr && (int)threadIdx.x < a.CO) ? a.bias[threadIdx.x] : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * threadIdx.x), "f"(bv));
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -116,146 +154,213 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   const int flush = a.flush_kb;
   const int chains_per_tile = (nkb + flush - 1) / flush;
 
-  if (warp == 0) {
-    // ===================== TMA producer: weight tiles =====================
-    if (ptx::elect_one()) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb; kb++, it++) {
-          const int s = it % kCtStages;
-          ptx::mbar_wait(empty_bar(s), ((it / kCtStages) & 1u) ^ 1u);
-          const uint32_t sb = stage_base(s);
-          ptx::mbar_arrive_expect_tx(full_b(s), 2 * b_bytes);
-          ptx::tma_load_2d(sb + OFF_BHI, &tmWhi, full_b(s), kb * 32, 0);
-          ptx::tma_load_2d(sb + OFF_BLO, &tmWlo, full_b(s), kb * 32, 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== UMMA issuer =====================
-    if (ptx::elect_one()) {
-      const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
-      const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
-      uint32_t it = 0, chain = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        int kb = 0;
-        for (int c = 0; c < chains_per_tile; c++, chain++) {
-          const int buf = chain & 1;
-          ptx::mbar_wait(tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
-          ptx::tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)a.NP;
-          const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
-          for (bool first = true; kb < kb_end; kb++, it++) {
-            const int s = it % kCtStages;
-            const uint32_t ph = (it / kCtStages) & 1u;
-            ptx::mbar_wait(full_a(s), ph);
-            ptx::mbar_wait(full_b(s), ph);
-            ptx::tc_fence_after();
+  // register budget (24 warps launched at 80 per thread = 61440): control warps 56, up to 16 gather warps 72 (idle
+  // ones 40), accumulate warps 136  (7168 + 36864 + 17408 = 61440)
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer: weight tiles (own ring, runs ahead of the operand stages) =====================
+      if (ptx::elect_one()) {
+        uint32_t it = 0;
+        long long w_eb = 0;
+        const long long tstart = clock64();
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+          for (int kb = 0; kb < nkb; kb++, it++) {
+            const int s = it % SB;
+            CT_TWAIT(w_eb, empty_b(s), ((it / SB) & 1u) ^ 1u);
             const uint32_t sb = stage_base(s);
+            ptx::mbar_arrive_expect_tx(full_b(s), 2 * b_bytes);
+            ptx::tma_load_2d(sb + OFF_BHI, &tmWhi, full_b(s), kb * 32, 0);
+            ptx::tma_load_2d(sb + OFF_BLO, &tmWlo, full_b(s), kb * 32, 0);
+          }
+        }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - tstart; a.dbg[1] = w_eb; }
+      }
+    } else if (warp == 1) {
+      // ===================== UMMA issuer: A from tensor memory, B from shared memory =====================
+      if (ptx::elect_one()) {
+        const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
+        const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
+        uint32_t it = 0, chain = 0;
+        long long w_te = 0, w_fa = 0, w_fb = 0;
+        const long long tstart = clock64();
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+          int kb = 0;
+          for (int c = 0; c < chains_per_tile; c++, chain++) {
+            const int buf = chain & 1;
+            CT_TWAIT(w_te, tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)buf * 64u;
+            const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
+            for (bool first = true; kb < kb_end; kb++, it++) {
+              const int sa = it % kCtAStages, sbi = it % SB;
+              CT_TWAIT(w_fa, full_a(sa), (it / kCtAStages) & 1u);
+              CT_TWAIT(w_fb, full_b(sbi), (it / SB) & 1u);
+              ptx::tc_fence_after();
+              const uint32_t sb = stage_base(sbi);
+              const uint32_t a_hi0 = tmem_base + (uint32_t)kCtAccCols + 64u * (uint32_t)sa, a_lo0 = a_hi0 + 32u;
 #pragma unroll
-            for (int k8 = 0; k8 < 4; k8++) {
-              const uint32_t koff = k8 * 32;
-              const uint64_t a_hi = ptx::umma_desc(dhi, sb + OFF_AHI + koff), a_lo = ptx::umma_desc(dhi, sb + OFF_ALO + koff);
-              const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff), b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
-              ptx::umma_tf32<1>(d, a_lo, b_hi, idesc, first ? 0u : 1u);
-              ptx::umma_tf32<1>(d, a_hi, b_lo, idesc, 1u);
-              ptx::umma_tf32<1>(d, a_hi, b_hi, idesc, 1u);
-              first = false;
+              for (int k8 = 0; k8 < 4; k8++) {
+                const uint32_t koff = k8 * 32;
+                const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff), b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
+                ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, b_hi, idesc, first ? 0u : 1u);
+                ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_lo, idesc, 1u);
+                ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_hi, idesc, 1u);
+                first = false;
+              }
+              ptx::umma_commit<1>(empty_a(sa));
+              ptx::umma_commit<1>(empty_b(sbi));
             }
-            ptx::umma_commit<1>(empty_bar(s));
+            ptx::umma_commit<1>(tfull_bar(buf));
           }
-          ptx::umma_commit<1>(tfull_bar(buf));
         }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[2] = clock64() - tstart; a.dbg[3] = w_te; a.dbg[4] = w_fa; a.dbg[5] = w_fb; }
+      }
+    } else if (warp == 3) {
+      // ===================== raw-image producer: whole images of the tile, one contiguous bulk copy =====================
+      if (ptx::elect_one()) {
+        uint32_t ti = 0;
+        long long w_re = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ti++) {
+          const int b = ti & 1;
+          CT_TWAIT(w_re, raw_empty(b), ((ti >> 1) & 1u) ^ 1u);
+          const int64_t p0 = (int64_t)tile * 128;
+          const int64_t p1 = (p0 + 127 < a.P - 1) ? p0 + 127 : a.P - 1;
+          const int64_t n0 = p0 / HW, n1 = p1 / HW;
+          const uint32_t bytes = (uint32_t)((n1 - n0 + 1) * a.CHW) * 4u;
+          ptx::mbar_arrive_expect_tx(raw_full(b), bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(raw_base + (uint32_t)b * a.raw_bytes), "l"(a.x + n0 * a.CHW), "r"(bytes), "r"(raw_full(b)) : "memory");
+        }
+        if (a.dbg && blockIdx.x == 0) a.dbg[6] = w_re;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== gather warps: build the im2col operand tile =====================
-    const int r = threadIdx.x - 128;                       // pixel row of the tile
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const int64_t p = (int64_t)tile * 128 + r;
+  } else if (warp < 4 + 4 * G) {
+    // ===================== gather groups: expand the raw images into the im2col operand (tensor memory) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int g = (warp - 4) >> 2;
+    const int r = (int)(threadIdx.x - 128) & 127;          // pixel row of the tile = TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kCtAccCols;
+    uint32_t ti = 0;
+    long long w_rf = 0, w_ea = 0, w_st = 0;
+    const long long tstart = clock64();
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ti++) {
+      const int64_t p0 = (int64_t)tile * 128;
+      const int64_t p = p0 + r;
       const bool pok = p < a.P;
-      const int64_t pp = pok ? p : 0;
-      const int64_t n = pp / ((int64_t)a.HO * a.WO);
-      const int rem = (int)(pp - n * (int64_t)a.HO * a.WO);
+      const int64_t pp = pok ? p : p0;
+      const int64_t n0 = p0 / HW;
+      const int64_t n = pp / HW;
+      const int rem = (int)(pp - n * HW);
       const int ho = rem / a.WO, wo = rem - ho * a.WO;
-      const int h0 = pok ? ho * a.sH - a.padH : -100000, w0 = wo * a.sW - a.padW;
-      const float* xb = a.x + n * (int64_t)a.C * a.H * a.W + (int64_t)h0 * a.W + w0;
-      for (int kb = 0; kb < nkb; kb++, it++) {
-        const int s = it % kCtStages;
-        ptx::mbar_wait(empty_bar(s), ((it / kCtStages) & 1u) ^ 1u);
-        const uint32_t sb = stage_base(s);
-        float v[32];
+      const int h0 = (pok || !CHECK) ? ho * a.sH - a.padH : -100000, w0 = wo * a.sW - a.padW;
+      const int b = ti & 1;
+      // byte address of (image n, channel 0, h0, w0) in the raw buffer (may point before the image when padded)
+      const uint32_t xb = raw_base + (uint32_t)b * a.raw_bytes + (uint32_t)(((int)(n - n0) * a.CHW + h0 * a.W + w0) * 4);
+      CT_TWAIT(w_rf, raw_full(b), (ti >> 1) & 1u);
+      for (int kb = g; kb < nkb; kb += G) {
+        const uint32_t it = ti * (uint32_t)nkb + (uint32_t)kb;
+        const int sa = it % kCtAStages;
+        CT_TWAIT(w_ea, empty_a(sa), ((it / kCtAStages) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t ta = t_lane + 64u * (uint32_t)sa;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          int ex, ey;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(tab_s + 8u * (uint32_t)(kb * 32 + j)));
-          const int h = h0 + (ey >> 16), w = w0 + (ey & 0xffff);
-          v[j] = ((unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W) ? __ldg(xb + ex) : 0.f;
-        }
+        for (int half = 0; half < 2; half++) {
+          float v[16];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          float hi4[4], lo4[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float xv = v[c * 4 + e];
-            float h = xv, l = 0.f;
-            if (isfinite(xv)) { h = ptx::to_tf32_rna(xv); l = ptx::to_tf32_rna(xv - h); }
-            hi4[e] = h; lo4[e] = l;
+          for (int j2 = 0; j2 < 8; j2++) {                 // two table entries per 128-bit broadcast load
+            int e0x, e0y, e1x, e1y;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0x), "=r"(e0y), "=r"(e1x), "=r"(e1y)
+                         : "r"(tab_s + 8u * (uint32_t)(kb * 32 + half * 16 + 2 * j2)));
+            float x0, x1;
+            if (CHECK) {
+              const int ha = h0 + (e0y >> 16), wa = w0 + (e0y & 0xffff), hb = h0 + (e1y >> 16), wb = w0 + (e1y & 0xffff);
+              x0 = 0.f; x1 = 0.f;
+              if ((unsigned)ha < (unsigned)a.H && (unsigned)wa < (unsigned)a.W) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(xb + 4u * (uint32_t)e0x));
+              if ((unsigned)hb < (unsigned)a.H && (unsigned)wb < (unsigned)a.W) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(xb + 4u * (uint32_t)e1x));
+            } else {
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(xb + 4u * (uint32_t)e0x));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(xb + 4u * (uint32_t)e1x));
+            }
+            v[2 * j2] = x0; v[2 * j2 + 1] = x1;
           }
-          const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);     // 128B swizzle: 16-byte chunk c of row r lands at c ^ (r & 7)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + OFF_AHI + off), "f"(hi4[0]), "f"(hi4[1]), "f"(hi4[2]), "f"(hi4[3]) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + OFF_ALO + off), "f"(lo4[0]), "f"(lo4[1]), "f"(lo4[2]), "f"(lo4[3]) : "memory");
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float h = ptx::to_tf32_rna(v[j]);
+            const float l = ptx::to_tf32_rna(v[j] - h);
+            hi[j] = __float_as_uint(h);
+            lo[j] = (fabsf(v[j]) < __int_as_float(0x7f800000)) ? __float_as_uint(l) : 0u;    // inf / nan: carried by hi alone
+          }
+          ptx::tmem_st_32x16(ta + 16u * half, hi);
+          ptx::tmem_st_32x16(ta + 32u + 16u * half, lo);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the UMMA (async proxy)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a(s)) : "memory");
+        { const long long t0_ = clock64(); ptx::tmem_st_wait(); w_st += clock64() - t0_; }
+        ptx::tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a(sa)) : "memory");
       }
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(raw_empty(b)) : "memory");   // done reading this tile's images
     }
-  } else if (warp >= 8) {
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[7] = clock64() - tstart; a.dbg[8] = w_rf; a.dbg[9] = w_ea; a.dbg[10] = w_st; }
+  } else if (warp < acc_warp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
     // ===================== accumulate / epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int q = warp & 3;
     const int r = q * 32 + (int)lane;                      // TMEM lane = pixel row of the tile
     uint32_t chain = 0;
+    long long w_tf = 0, w_ep = 0;
+    const long long tstart = clock64();
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; i++) acc[i] = 0.f;
       for (int c = 0; c < chains_per_tile; c++, chain++) {
         const int buf = chain & 1;
-        ptx::mbar_wait(tfull_bar(buf), (chain >> 1) & 1u);
+        CT_TWAIT(w_tf, tfull_bar(buf), (chain >> 1) & 1u);
         ptx::tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)a.NP;
-        if (a.NP > 32) {
-          uint32_t r0[32], r1[32];
-          ptx::tmem_ld_32x32(t0, r0);
-          ptx::tmem_ld_32x32(t0 + 32, r1);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) { acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i])); acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i])); }
-        } else {
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 64u;
+        {
           uint32_t r0[32];
           ptx::tmem_ld_32x32(t0, r0);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
         }
+        if (a.NP > 32) {
+          uint32_t r1[32];
+          ptx::tmem_ld_32x32(t0 + 32, r1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i]));
+        }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
       }
       // epilogue: out[n][co][ho][wo] = acc[co] + bias[co]; consecutive lanes = consecutive pixels
+      const long long te_ = clock64();
       const int64_t p = (int64_t)tile * 128 + r;
       if (p < a.P) {
-        const int64_t hw = (int64_t)a.HO * a.WO;
-        const int64_t n = p / hw, rem = p - n * hw;
-        float* yp = a.y + n * a.CO * hw + rem;
+        const int64_t n = p / HW, rem = p - n * HW;
+        float* yp = a.y + n * a.CO * HW + rem;
+        // the bias comes from shared memory: a global load here could alias the stores and would serialise them
 #pragma unroll
-        for (int co = 0; co < 64; co++)
-          if (co < a.CO) yp[co * hw] = __fadd_rn(acc[co], a.bias ? a.bias[co] : 0.f);
+        for (int c4 = 0; c4 < 16; c4++) {
+          if (c4 * 4 < a.CO) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_s + 16u * c4));
+            const float bb[4] = {b0, b1, b2, b3};
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (c4 * 4 + e < a.CO) yp[(c4 * 4 + e) * HW] = __fadd_rn(acc[c4 * 4 + e], bb[e]);
+          }
+        }
       }
+      w_ep += clock64() - te_;
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[11] = clock64() - tstart; a.dbg[12] = w_tf; a.dbg[13] = w_ep; }
   }
 
   __syncwarp();
@@ -282,12 +387,24 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   const int K = v.C * v.kH * v.kW;
   if (v.CO > 64 || K > 4096) return AM_OK;                       // accumulators: 64 registers per pixel; table in smem
   if (v.kH * v.dH >= 32767 || v.kW * v.dW >= 32767) return AM_OK;
-  if ((int64_t)v.C * v.H * v.W >= (1ll << 31)) return AM_OK;
+  const int64_t CHW = (int64_t)v.C * v.H * v.W;
+  // whole input images are staged in shared memory by 16-byte bulk copies
+  if (CHW % 4 != 0 || (reinterpret_cast<uintptr_t>(v.x) & 15) != 0) return AM_OK;
   const int64_t P = v.N * (int64_t)v.HO * v.WO;
   if (P <= 0 || P >= (1ll << 37)) return AM_OK;
   const int Kpad = (int)round_up(K, 32), nkb = Kpad / 32;
   const int NP = (int)round_up(v.CO, 16);
   const int Rpad = 64;                                            // weight planes padded to 64 rows
+  // shared-memory plan: weight ring + two raw-image buffers + barriers + k table (the im2col operand lives in TMEM)
+  const int64_t HWo = (int64_t)v.HO * v.WO;
+  const int64_t max_imgs = (128 % HWo == 0) ? 128 / HWo : 127 / HWo + 2;      // images one 128-pixel tile can touch
+  const int64_t raw_bytes = round_up(max_imgs * CHW * 4, 128);
+  const size_t stage_bytes = 2 * (size_t)NP * 128;
+  const size_t fixed = 1024 + 8 * 38 + 256 + (size_t)Kpad * 8 + 64 + 2 * (size_t)raw_bytes;
+  if (fixed + 2 * stage_bytes > 227 * 1024) return AM_OK;
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (stages > kCtMaxBStages) stages = kCtMaxBStages;
+  const bool checked = v.padH != 0 || v.padW != 0;
   // workspace: weight hi/lo planes + k table
   void* ws = nullptr;
   const size_t plane = (size_t)Rpad * Kpad * sizeof(float);
@@ -297,7 +414,8 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   int2* tab = (int2*)((char*)ws + 2 * plane);
   conv_tc_pack_weights_kernel<<<(unsigned)ceil_div((int64_t)Rpad * Kpad, 256), 256, 0, st>>>(
       v.w, whi, wlo, v.CO, Rpad, K, Kpad, v.C, v.kH, v.kW, v.w_off, v.w_sco, v.w_sci, v.w_skh, v.w_skw);
-  conv_tc_table_kernel<<<(unsigned)ceil_div(Kpad, 256), 256, 0, st>>>(tab, K, Kpad, v.kH, v.kW, v.H, v.W, v.dH, v.dW);
+
+  conv_tc_table_kernel<<<(unsigned)ceil_div(Kpad, 256), 256, 0, st>>>(tab, K, Kpad, v.kH, v.kW, v.H, v.W, v.dH, v.dW, checked ? 1 : 0);
   g_launch_count += 2;
   AM_CUDA_TRY(cudaGetLastError());
 
@@ -319,21 +437,45 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
     if (r != CUDA_SUCCESS) { set_last_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AM_ERR_CUDA; }
   }
   ConvTcArgs a{};
-  a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P;
+  a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N;
+  a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes;
+  static int groups_env = 0;
+  if (groups_env == 0) { const char* e = getenv("AM_CONVTC_GROUPS"); groups_env = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4; }
+  a.groups = groups_env;
+  static int dbg_env = -1;
+  if (dbg_env < 0) { const char* e = getenv("AM_CONVTC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+  a.dbg = nullptr;
+  if (dbg_env) {
+    void* base = nullptr;
+    if ((rc = workspace(kWsMisc, 64 * sizeof(int) + 1024, &base))) return rc;
+    a.dbg = (long long*)((char*)base + 512);
+    AM_CUDA_TRY(cudaMemsetAsync(a.dbg, 0, 16 * sizeof(long long), st));
+  }
   a.C = v.C; a.H = v.H; a.W = v.W; a.CO = v.CO; a.HO = v.HO; a.WO = v.WO; a.padH = v.padH; a.padW = v.padW; a.sH = v.sH; a.sW = v.sW;
   a.K = K; a.kblocks = nkb; a.NP = NP;
   static int flush_env = -1;
   if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
   a.flush_kb = flush_env;
   a.ntiles = (int)ceil_div(P, 128);
-  const size_t stage_bytes = 2 * (size_t)kCtABytes + 2 * (size_t)NP * 128;
-  const size_t smem = kCtStages * stage_bytes + 1024 + 8 * (3 * kCtStages + 6) + (size_t)Kpad * 8 + 64;
-  if (smem > 227 * 1024) return AM_OK;
-  AM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
   const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-  conv_tc_kernel<<<grid, 384, smem, st>>>(tms[0], tms[1], a);
+  const int nthreads = 768;
+  if (checked) {
+    AM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<true><<<grid, nthreads, smem, st>>>(tms[0], tms[1], a);
+  } else {
+    AM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<false><<<grid, nthreads, smem, st>>>(tms[0], tms[1], a);
+  }
   g_launch_count++;
   AM_CUDA_TRY(cudaGetLastError());
+  if (a.dbg) {
+    long long h[16];
+    AM_CUDA_TRY(cudaMemcpyAsync(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    AM_CUDA_TRY(cudaStreamSynchronize(st));
+    fprintf(stderr, "[conv_tc dbg] tiles/cta=%d nkb=%d SB=%d | tma: total %lld wait_empty_b %lld | mma: total %lld wait_tempty %lld wait_full_a %lld wait_full_b %lld | raw: wait_raw_empty %lld | gather0: total %lld wait_raw_full %lld wait_empty_a %lld wait_st %lld | acc: total %lld wait_tfull %lld epilogue %lld\n",
+            (a.ntiles + grid - 1) / grid, a.kblocks, a.stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
+  }
   *done = true;
   return AM_OK;
 }

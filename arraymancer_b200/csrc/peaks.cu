@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 
 // back-to-back tcgen05.mma kind::tf32 on resident smem operands: pure tensor-pipe rate
 template <int CG>
-__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int batch) {
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int batch, int n_mma, int nacc, int a_in_tmem) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 8;
@@ -93,12 +93,16 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int batch)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
   if (warp == 0 && leader && ptx::elect_one()) {
     const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
-    const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, 256);
+    const uint32_t idesc = ptx::umma_idesc_tf32(128 * CG, (uint32_t)n_mma);
     uint32_t ph = 0;
     for (int it = 0; it < iters; it++) {
       for (int j = 0; j < batch; j++) {
         const uint32_t koff = (uint32_t)(j & 3) * 32;
-        ptx::umma_tf32<CG>(tmem, ptx::umma_desc(dhi, a_s + koff), ptx::umma_desc(dhi, b_s + koff), idesc, (it | j) ? 1u : 0u);
+        // nacc > 1: consecutive MMAs go to different accumulators (no dependency between neighbours)
+        const uint32_t d = tmem + (uint32_t)(j % nacc) * (uint32_t)n_mma;
+        const uint32_t en = (it | (j >= nacc)) ? 1u : 0u;
+        if (CG == 1 && a_in_tmem) ptx::umma_tf32_ts(d, tmem + 224u + 8u * (j & 3), ptx::umma_desc(dhi, b_s + koff), idesc, en);
+        else ptx::umma_tf32<CG>(d, ptx::umma_desc(dhi, a_s + koff), ptx::umma_desc(dhi, b_s + koff), idesc, en);
       }
       // single-CTA arrive even for CG == 2: only the leader waits
       asm volatile("tcgen05.commit.cta_group::%1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar), "n"(CG) : "memory");
@@ -176,10 +180,15 @@ int microbench(int which, double* tops) {
       ops = 2.0 * CH * (double)iters * blocks * threads;
     } break;
     case 5:
-    case 6: {
+    case 6:
+    case 8: case 9: case 10: case 11: case 12: {   // 8..12: small-N variants (what the implicit-GEMM conv issues)
       if (!gemm_f32_tc_available()) { set_last_error("microbench: tcgen05 needs compute capability 10.x"); return AM_ERR_UNSUPPORTED; }
-      const int cg = which == 5 ? 1 : 2;
+      const int cg = which == 6 ? 2 : 1;
       const int iters = 2000, batch = 16;
+      // 8: N=64 one accumulator | 9: N=64 two accumulators | 10: N=64, A from TMEM | 11: N=64, A from TMEM, 2 acc | 12: N=128
+      const int n_mma = (which >= 8 && which <= 11) ? 64 : (which == 12 ? 128 : 256);
+      const int nacc = (which == 9 || which == 11) ? 2 : 1;
+      const int ts = (which == 10 || which == 11) ? 1 : 0;
       const int smem = 16384 + 32768 + 64 + 1024;
       auto k1 = umma_peak_kernel<1>;
       auto k2 = umma_peak_kernel<2>;
@@ -193,10 +202,10 @@ int microbench(int which, double* tops) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (cg == 1) cudaLaunchKernelEx(&cfg, k1, iters, batch); else cudaLaunchKernelEx(&cfg, k2, iters, batch);
+        if (cg == 1) cudaLaunchKernelEx(&cfg, k1, iters, batch, n_mma, nacc, ts); else cudaLaunchKernelEx(&cfg, k2, iters, batch, n_mma, nacc, ts);
         g_launch_count++;
       }, 3, &ms);
-      ops = 2.0 * (128.0 * cg) * 256.0 * 8.0 * (double)iters * batch * (grid / cg);
+      ops = 2.0 * (128.0 * cg) * (double)n_mma * 8.0 * (double)iters * batch * (grid / cg);
     } break;
     default:
       set_last_error("microbench: unknown selector %d", which);

@@ -44,6 +44,12 @@ def exp_peaks():
     return res
 
 
+def exp_peaks_small_n():
+    from arraymancer_b200 import _capi
+    names = {8: "umma_n64", 9: "umma_n64_2acc", 10: "umma_n64_ts", 11: "umma_n64_ts_2acc", 12: "umma_n128"}
+    return {n: _capi.microbench(i) for i, n in names.items()}
+
+
 def _rand(shape, dt, seed):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -228,6 +234,8 @@ def exp_conv_speed():
     import torch
     import arraymancer_b200 as am
     res = {}
+    if os.environ.get("AM_BRINGUP_CONV_PATH"):
+        am._capi.set_conv_path(int(os.environ["AM_BRINGUP_CONV_PATH"]))
     for name, xs, ks in [("cv1", (4096, 1, 28, 28), (20, 1, 5, 5)), ("cv2", (4096, 20, 12, 12), (50, 20, 5, 5))]:
         X = torch.rand(xs, device="cuda"); K_ = torch.randn(ks, device="cuda") * 0.1; B_ = torch.zeros(ks[0], 1, 1, device="cuda")
         out = am.conv2d(X, K_, B_)
@@ -242,7 +250,7 @@ def exp_conv_speed():
     return res
 
 
-EXPERIMENTS = ["peaks", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed", "f64_speed",
+EXPERIMENTS = ["peaks", "peaks_small_n", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed", "f64_speed",
                "tc1_speed_f2", "tc2_speed_f1", "tc2_speed_f2", "tc2_speed_f4", "tc2_speed_f8", "conv_speed"]
 
 

@@ -41,7 +41,9 @@ if what == "i64wide":
     torch.cuda.synchronize()
 if what in ("tc", "all"):
     gemm(torch.float32, 8192, am.F32_TC)
-if what in ("conv", "all"):
+if what == "convtc":
+    am._capi.set_conv_path(am._capi.CONV_TC)
+if what in ("conv", "convtc", "all"):
     for xs, ks in [((4096, 1, 28, 28), (20, 1, 5, 5)), ((4096, 20, 12, 12), (50, 20, 5, 5))]:
         X = torch.rand(xs, device="cuda"); W = torch.randn(ks, device="cuda") * 0.1; B = torch.zeros(ks[0], 1, 1, device="cuda")
         for _ in range(reps):

@@ -308,10 +308,11 @@ int conv2d_dgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
                         const float* kernel, float* grad_input, bool* done);
 // conv_tc_bwd.cu: data gradient as GEMM + col2im on the tensor cores (any stride / padding / dilation, Cout <= 64)
 int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
-                               const float* kernel, float* grad_input, bool* done);
+                               const float* kernel, float* grad_input, bool only_if_fast, bool* done);
 std::atomic<int> g_conv_path{AM_CONV_AUTO};
 static bool direct_enabled() { return g_conv_path.load() != AM_CONV_GATHER; }
 static bool tc_enabled() { return g_conv_path.load() == AM_CONV_TC; }
+static bool auto_path() { return g_conv_path.load() == AM_CONV_AUTO; }
 
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
@@ -321,7 +322,8 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   if (g.Nimg == 0) return AM_OK;
   if (!input || !kernel || !output) { set_last_error("conv2d_forward: null pointer"); return AM_ERR_INVALID; }
   if constexpr (std::is_same<T, float>::value) {
-    if (tc_enabled()) {
+    // AUTO: the tcgen05 implicit GEMM pays once the GEMM is wide and deep enough (measured: LeNet cv2 yes, cv1 no)
+    if (tc_enabled() || (auto_path() && d.Cout >= 32 && g.Kc >= 128)) {
       bool done = false;
       int rcd = conv2d_forward_tc_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
       if (rcd || done) return rcd;
@@ -360,10 +362,10 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
 
   bool dgrad_done = false;
   if constexpr (std::is_same<T, float>::value) {
-    if (grad_input && g.Nimg > 0 && tc_enabled()) {
+    if (grad_input && g.Nimg > 0 && (tc_enabled() || auto_path())) {
       static const bool gather_form = getenv("AM_CONVTC_DGRAD_GATHER") != nullptr;      // older gather-form kernel (comparison)
-      if (gather_form) rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
-      else rc = conv2d_dgrad_col2im_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      if (gather_form && tc_enabled()) rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
+      else rc = conv2d_dgrad_col2im_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, !tc_enabled(), &dgrad_done);
       if (rc) return rc;
     }
     if (grad_input && g.Nimg > 0 && !dgrad_done && direct_enabled()) {

@@ -287,10 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            const float h = ptx::to_tf32_rna(v[j]);
-            const float l = ptx::to_tf32_rna(v[j] - h);
-            hi[j] = __float_as_uint(h);
-            lo[j] = (fabsf(v[j]) < __int_as_float(0x7f800000)) ? __float_as_uint(l) : 0u;    // inf / nan: carried by hi alone
+            ptx::split_tf32(v[j], hi[j], lo[j]);
           }
           ptx::tmem_st_32x16(ta + 16u * half, hi);
           ptx::tmem_st_32x16(ta + 32u + 16u * half, lo);

@@ -193,10 +193,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            const float h = ptx::to_tf32_rna(v[j]);
-            const float l = ptx::to_tf32_rna(v[j] - h);
-            hi[j] = __float_as_uint(h);
-            lo[j] = (fabsf(v[j]) < __int_as_float(0x7f800000)) ? __float_as_uint(l) : 0u;
+            ptx::split_tf32(v[j], hi[j], lo[j]);
           }
           ptx::tmem_st_32x16(ta + (uint32_t)c0, hi);
           ptx::tmem_st_32x16(ta + (uint32_t)a.Kpad + (uint32_t)c0, lo);
@@ -505,6 +502,408 @@ int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t
     fprintf(stderr, "[dgrad_tc dbg] grid=%d chunks=%d cpc=%d ipg=%d tpg=%d groups/cta~%lld | mma: total %lld wait_d_empty %lld wait_a_full %lld | operand: total %lld wait_a_empty %lld | col2im: total %lld wait_d_full %lld phase1 %lld phase2 %lld flush %lld\n",
             grid, a.nchunks, a.cpc, a.ipg, a.tpg, (long long)(a.ngroups * a.nchunks / grid), h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
   }
+  *done = true;
+  return AM_OK;
+}
+
+
+// =====================================================================================================================
+// Weight gradient on the tensor cores: the forward implicit GEMM with the roles of "pixels" and "k" exchanged,
+//
+//   dW[R, co] = sum over images n and output pixels q of  col[n, R, q] * gout[n, co, q],   R = (ci, kh, kw)  (M, TMEM lanes)
+//
+// (conv.nim:140  gW += gout[i] * col^T, summed over the batch).  Row R = Kc is a row of ones, so column... row Kc of the
+// result is grad_bias (nnp_convolution.nim:91-94).  A CTA owns one chunk of 128 rows R and a slice of the batch; per
+// stage of 32 pixels the gather groups expand the staged input channels into the A operand IN TENSOR MEMORY
+// (lane = row R, column = pixel), the loader warps split the matching gout block [co x 32 pixels] into tf32 hi / lo and
+// write it K-major / 128B-swizzled into shared memory (B operand), and one thread issues 12 tcgen05.mma.  Chains of
+// `flush_st` stages go to one of two TMEM accumulators and are drained into fp32 registers with round-to-nearest adds
+// (the tensor core truncates when it accumulates).  Partial sums per batch slice go to part[slice][co][Nv]; the
+// existing fixed-order wgrad_reduce_kernel adds the slices (deterministic).
+struct WgradTcArgs {
+  const float* x;       // [N][C][H][W]
+  const float* gout;    // [N][CO][HO][WO]
+  float* part;          // [nslices][CO][Nv]
+  int64_t N;
+  int C, H, W, CO, HO, WO, kH, kW, padH, padW, sH, sW, dH, dW;
+  int Kc, Nv;           // C*kH*kW, Kc + 1 (the ones row)
+  int NP;               // Cout padded to 16 / 32 / 64: UMMA N
+  int nchunks, nslices;
+  int spi;              // stages of 32 pixels per image
+  int flush_st;         // stages per accumulation chain
+  int SB;               // depth of the gout ring
+  int groups;           // gather groups (of 128 threads), <= 3
+  uint32_t raw_bytes;   // bytes of one staged-input buffer
+  int checked;          // the convolution has padding: bounds test per gathered element
+  int vec;              // gout rows can be read with 128-bit loads
+  long long* dbg;       // optional per-role cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
+};
+
+constexpr int kWgAStages = 6;
+#define WG_TWAIT(counter, bar, ph) do { const long long t0_ = clock64(); ptx::mbar_wait(bar, ph); counter += clock64() - t0_; } while (0)
+
+
+__global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)a.NP * 128u;                     // one plane of a gout stage: NP rows x 32 pixels
+  const uint32_t stage_bytes = 2u * b_bytes;
+  const int SB = a.SB;
+  const uint32_t raw_base = smem_base + (uint32_t)SB * stage_bytes;
+  const uint32_t bar_base = raw_base + 2u * a.raw_bytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };               // 6
+  auto empty_a = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
+  auto full_b = [&](int s) { return bar_base + 8u * (12 + s); };        // 8
+  auto empty_b = [&](int s) { return bar_base + 8u * (20 + s); };       // 8
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (28 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (30 + b); };
+  auto raw_full = [&](int b) { return bar_base + 8u * (32 + b); };
+  auto raw_empty = [&](int b) { return bar_base + 8u * (34 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 36;
+  const uint32_t ptab = bar_base + 8u * 38;                               // int2 per output pixel: {byte offset of (h0, w0), h0 | w0 << 16}
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = ptx::lane_id();
+  const int G = a.groups;
+  const int KK = a.kH * a.kW, HWi = a.H * a.W, HWo = a.HO * a.WO;
+  const int chunk = (int)blockIdx.x % a.nchunks, slice = (int)blockIdx.x / a.nchunks;
+  for (int q = threadIdx.x; q < a.spi * 32; q += blockDim.x) {            // pixel walk of an image, shared by all rows
+    const int ho = q / a.WO, wo = q - ho * a.WO;
+    const int h0 = ho * a.sH - a.padH, w0 = wo * a.sW - a.padW;
+    const int e0 = (q < HWo) ? (h0 * a.W + w0) * 4 : 0, e1 = (q < HWo) ? ((h0 & 0xffff) | (w0 << 16)) : 0x7fff7fff;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptab + 8u * q), "r"(e0), "r"(e1) : "memory");
+  }
+  const int R0 = chunk * 128;
+  const int64_t nimg = (a.N > slice) ? (a.N - slice + a.nslices - 1) / a.nslices : 0;    // images slice, slice + nslices, ...
+  const int64_t T = nimg * a.spi;                                         // stages this CTA walks through
+  // input channels this chunk's rows touch
+  const int Rl = (R0 < a.Kc) ? R0 : a.Kc - 1, Rh = (R0 + 127 < a.Kc) ? R0 + 127 : a.Kc - 1;
+  const int ci_first = Rl / KK, nci = Rh / KK - ci_first + 1;
+
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kWgAStages; s++) { ptx::mbar_init(full_a(s), 128); ptx::mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < SB; s++) { ptx::mbar_init(full_b(s), 128); ptx::mbar_init(empty_b(s), 1); }
+    for (int b = 0; b < 2; b++) {
+      ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4);
+      ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_a0 = tmem_base + 128u;                              // 6 operand stages of 64 columns after the accumulators
+
+  // register budget (24 warps at 80): control 56, gather / loader warps 72, accumulate warps 136
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== staged-input producer: the chunk's channels of one image per bulk copy =====================
+      if (ptx::elect_one()) {
+        const uint32_t bytes = (uint32_t)(nci * HWi) * 4u;
+        for (int64_t i = 0; i < nimg; i++) {
+          const int b = (int)(i & 1);
+          ptx::mbar_wait(raw_empty(b), (uint32_t)((i >> 1) & 1) ^ 1u);
+          const int64_t n = slice + i * a.nslices;
+          ptx::mbar_arrive_expect_tx(raw_full(b), bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(raw_base + (uint32_t)b * a.raw_bytes), "l"(a.x + (n * a.C + ci_first) * (int64_t)HWi), "r"(bytes), "r"(raw_full(b)) : "memory");
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== UMMA issuer =====================
+      if (ptx::elect_one()) {
+        const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
+        const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
+        uint32_t chain = 0;
+        long long w_te = 0, w_fa = 0, w_fb = 0;
+        const long long tstart = clock64();
+        for (int64_t it = 0; it < T; it++) {
+          const int in_chain = (int)(it % a.flush_st);
+          const int buf = chain & 1;
+          if (in_chain == 0) {
+            WG_TWAIT(w_te, tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+          }
+          const int sa = (int)(it % kWgAStages), sbi = (int)(it % SB);
+          WG_TWAIT(w_fa, full_a(sa), (uint32_t)((it / kWgAStages) & 1));
+          WG_TWAIT(w_fb, full_b(sbi), (uint32_t)((it / SB) & 1));
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)buf * 64u;
+          const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
+          const uint32_t a_hi0 = tmem_a0 + 64u * (uint32_t)sa, a_lo0 = a_hi0 + 32u;
+#pragma unroll
+          for (int k8 = 0; k8 < 4; k8++) {
+            const uint64_t b_hi = ptx::umma_desc(dhi, sb + k8 * 32), b_lo = ptx::umma_desc(dhi, sb + b_bytes + k8 * 32);
+            ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, b_hi, idesc, (in_chain | k8) ? 1u : 0u);
+            ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_lo, idesc, 1u);
+            ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_hi, idesc, 1u);
+          }
+          ptx::umma_commit<1>(empty_a(sa));
+          ptx::umma_commit<1>(empty_b(sbi));
+          if (in_chain == a.flush_st - 1 || it == T - 1) { ptx::umma_commit<1>(tfull_bar(buf)); chain++; }
+        }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - tstart; a.dbg[1] = w_te; a.dbg[2] = w_fa; a.dbg[3] = w_fb; }
+      }
+    }
+  } else if (warp < 4 + 4 * G) {
+    // ===================== gather groups: A[R, pixel] -> tensor memory =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int g = (warp - 4) >> 2;
+    const int r = (int)(threadIdx.x - 128) & 127;
+    const int R = R0 + r;
+    const uint32_t t_lane = tmem_a0 + ((uint32_t)((warp & 3) * 32) << 16);
+    int kind = 0, base = 0, khd = 0, kwd = 0;            // 0: zero row, 1: tap row, 2: ones row (grad_bias)
+    if (R < a.Kc) {
+      const int ci = R / KK, tap = R - ci * KK, kh = tap / a.kW, kw = tap - kh * a.kW;
+      kind = 1; khd = kh * a.dH; kwd = kw * a.dW;
+      base = (ci - ci_first) * HWi + khd * a.W + kwd;
+    } else if (R == a.Kc) {
+      kind = 2;
+    }
+    long long w_rf = 0, w_ea = 0;
+    const long long tstart = clock64();
+    for (int64_t i = 0; i < nimg; i++) {
+      const int b = (int)(i & 1);
+      WG_TWAIT(w_rf, raw_full(b), (uint32_t)((i >> 1) & 1));      // every group waits for every image (keeps the phases of raw_empty in step)
+      const uint32_t xb = raw_base + (uint32_t)b * a.raw_bytes + (uint32_t)(base * 4);
+      for (int s = 0; s < a.spi; s++) {
+        const int64_t it = i * a.spi + s;
+        if ((int)(it % G) != g) continue;
+        const int sa = (int)(it % kWgAStages);
+        WG_TWAIT(w_ea, empty_a(sa), (uint32_t)((it / kWgAStages) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t ta = t_lane + 64u * (uint32_t)sa;
+        const int q0 = s * 32;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          float v[16];
+          if (kind == 1) {
+#pragma unroll
+            for (int j2 = 0; j2 < 8; j2++) {                   // two pixel-table entries per 128-bit broadcast load
+              int e0x, e0y, e1x, e1y;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0x), "=r"(e0y), "=r"(e1x), "=r"(e1y)
+                           : "r"(ptab + 8u * (uint32_t)(q0 + half * 16 + 2 * j2)));
+              float x0 = 0.f, x1 = 0.f;
+              if (a.checked) {
+                // the table holds h0 / w0 as 16-bit fields (0x7fff for pixels past the image: never in range)
+                const int ha = (int)(short)(e0y & 0xffff) + khd, wa = (e0y >> 16) + kwd;
+                const int hb = (int)(short)(e1y & 0xffff) + khd, wb = (e1y >> 16) + kwd;
+                if ((unsigned)ha < (unsigned)a.H && (unsigned)wa < (unsigned)a.W) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(xb + (uint32_t)e0x));
+                if ((unsigned)hb < (unsigned)a.H && (unsigned)wb < (unsigned)a.W) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(xb + (uint32_t)e1x));
+              } else {
+                if (q0 + half * 16 + 2 * j2 < HWo) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(xb + (uint32_t)e0x));
+                if (q0 + half * 16 + 2 * j2 + 1 < HWo) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(xb + (uint32_t)e1x));
+              }
+              v[2 * j2] = x0; v[2 * j2 + 1] = x1;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = (kind == 2 && q0 + half * 16 + j < HWo) ? 1.f : 0.f;
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            ptx::split_tf32(v[j], hi[j], lo[j]);
+          }
+          ptx::tmem_st_32x16(ta + 16u * half, hi);
+          ptx::tmem_st_32x16(ta + 32u + 16u * half, lo);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a(sa)) : "memory");
+      }
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(raw_empty(b)) : "memory");
+    }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[4] = clock64() - tstart; a.dbg[5] = w_rf; a.dbg[6] = w_ea; }
+  } else if (warp < 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // unused gather slots
+  } else if (warp < 20) {
+    // ===================== loader warps: gout block [co x 32 pixels] -> tf32 hi/lo, K-major swizzled smem =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int t = (int)threadIdx.x - 512;                       // 0..127
+    const int tpr = 128 / a.NP;                                 // threads per row: 2, 4 or 8
+    const int co = t / tpr, part = t - co * tpr;
+    const int ppt = 32 / tpr;                                   // pixels per thread: 16, 8 or 4
+    const uint32_t row_off = (uint32_t)co * 128u, sw = (uint32_t)(co & 7);
+    const int nv = ppt / 4;                                     // 128-bit pieces per thread and stage: 1, 2 or 4
+    // global loads of stage it + 1 are in flight while stage it is split and stored (the loader is otherwise
+    // latency-bound: one dependent L2 round trip per stage)
+    auto fetch = [&](int64_t it, float4 (&dst)[4]) {
+      const int64_t i = it / a.spi;
+      const int s = (int)(it - i * a.spi);
+      const int64_t n = slice + i * a.nslices;
+      const int q0 = s * 32 + part * ppt;
+      const float* src = a.gout + (n * a.CO + co) * (int64_t)HWo + q0;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; v4++) {
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int q = q0 + 4 * v4;
+        if (v4 < nv && co < a.CO) {
+          if (a.vec) {
+            if (q < HWo) f = __ldg(reinterpret_cast<const float4*>(src + 4 * v4));
+          } else {
+            if (q < HWo) f.x = __ldg(src + 4 * v4);
+            if (q + 1 < HWo) f.y = __ldg(src + 4 * v4 + 1);
+            if (q + 2 < HWo) f.z = __ldg(src + 4 * v4 + 2);
+            if (q + 3 < HWo) f.w = __ldg(src + 4 * v4 + 3);
+          }
+        }
+        dst[v4] = f;
+      }
+    };
+    float4 cur[4], nxt[4];
+    if (T > 0) fetch(0, cur);
+    long long w_eb = 0;
+    const long long tstart = clock64();
+    for (int64_t it = 0; it < T; it++) {
+      if (it + 1 < T) fetch(it + 1, nxt);
+      const int sbi = (int)(it % SB);
+      WG_TWAIT(w_eb, empty_b(sbi), (uint32_t)((it / SB) & 1) ^ 1u);
+      const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; v4++) {
+        if (v4 < nv) {
+          const float v[4] = {cur[v4].x, cur[v4].y, cur[v4].z, cur[v4].w};
+          float h4[4], l4[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            uint32_t hb, lb;
+            ptx::split_tf32(v[e], hb, lb);
+            h4[e] = __uint_as_float(hb); l4[e] = __uint_as_float(lb);
+          }
+          const uint32_t c16 = (uint32_t)(part * nv + v4);                  // 16-byte chunk of the 128-byte row
+          const uint32_t off = row_off + ((c16 ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(h4[0]), "f"(h4[1]), "f"(h4[2]), "f"(h4[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + b_bytes + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b(sbi)) : "memory");
+#pragma unroll
+      for (int v4 = 0; v4 < 4; v4++) cur[v4] = nxt[v4];
+    }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[7] = clock64() - tstart; a.dbg[8] = w_eb; }
+  } else {
+    // ===================== accumulate warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int qd = warp & 3;
+    const int r = qd * 32 + (int)lane;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc[i] = 0.f;
+    const int64_t nchains = (T + a.flush_st - 1) / a.flush_st;
+    long long w_tf = 0;
+    const long long tstart = clock64();
+    for (int64_t c = 0; c < nchains; c++) {
+      const int buf = (int)(c & 1);
+      WG_TWAIT(w_tf, tfull_bar(buf), (uint32_t)((c >> 1) & 1));
+      ptx::tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)buf * 64u;
+      {
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(t0, r0);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
+      }
+      if (a.NP > 32) {
+        uint32_t r1[32];
+        ptx::tmem_ld_32x32(t0 + 32, r1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i]));
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+    }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[9] = clock64() - tstart; a.dbg[10] = w_tf; }
+    const int R = R0 + r;
+    if (R < a.Nv) {
+      float* dst = a.part + (int64_t)slice * a.CO * a.Nv + R;
+#pragma unroll
+      for (int co = 0; co < 64; co++)
+        if (co < a.CO) dst[(int64_t)co * a.Nv] = acc[co];
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 512);
+}
+
+// partial weight / bias gradients per batch slice on the tensor cores; *done == false -> shape does not fit
+int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                        const float* grad_output, float** part_out, int* groups_out, bool* done) {
+  *done = false;
+  if (!gemm_f32_tc_available()) return AM_OK;
+  const int KK = (int)(d.kH * d.kW);
+  if (d.Cout > 64 || d.Cout < 1 || KK < 1) return AM_OK;
+  if (d.H * d.W >= (1 << 20) || Ho * Wo >= (1 << 20) || d.C * (int64_t)KK >= (1 << 24)) return AM_OK;
+  if (d.H >= 32000 || d.W >= 32000) return AM_OK;                          // 16-bit fields of the pixel table
+  const int HWi = (int)(d.H * d.W), HWo = (int)(Ho * Wo);
+  if (HWi % 4 != 0 || (reinterpret_cast<uintptr_t>(input) & 15) != 0) return AM_OK;     // 16-byte bulk copies of whole channels
+  WgradTcArgs a{};
+  a.x = input; a.gout = grad_output; a.N = d.N;
+  a.C = (int)d.C; a.H = (int)d.H; a.W = (int)d.W; a.CO = (int)d.Cout; a.HO = (int)Ho; a.WO = (int)Wo;
+  a.kH = (int)d.kH; a.kW = (int)d.kW; a.padH = (int)d.padH; a.padW = (int)d.padW; a.sH = (int)d.strideH; a.sW = (int)d.strideW;
+  a.dH = (int)d.dilH; a.dW = (int)d.dilW;
+  a.Kc = a.C * KK; a.Nv = a.Kc + 1;
+  a.NP = a.CO <= 16 ? 16 : (a.CO <= 32 ? 32 : 64);
+  a.nchunks = (a.Nv + 127) / 128;
+  const int sms = sm_count();
+  if (a.nchunks > sms) return AM_OK;
+  a.nslices = sms / a.nchunks;
+  if ((int64_t)a.nslices > d.N) a.nslices = (int)d.N;
+  if (a.nslices < 1) a.nslices = 1;
+  a.spi = (HWo + 31) / 32;
+  static int flush_env = -1, groups_env = 0;
+  if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
+  if (groups_env == 0) { const char* e = getenv("AM_CONVTC_GROUPS"); groups_env = (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 3; }
+  a.flush_st = flush_env;
+  a.groups = groups_env > 3 ? 3 : groups_env;
+  a.checked = (a.padH != 0 || a.padW != 0) ? 1 : 0;
+  a.vec = (HWo % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_output) & 15) == 0) ? 1 : 0;
+  const int nci_max = 127 / KK + 2 < a.C ? 127 / KK + 2 : a.C;
+  a.raw_bytes = (uint32_t)round_up((int64_t)nci_max * HWi * 4, 128);
+  const size_t stage_bytes = 2 * (size_t)a.NP * 128;
+  const size_t fixed = 1024 + 2 * (size_t)a.raw_bytes + 8 * 38 + (size_t)a.spi * 32 * 8 + 64;
+  if (fixed + 2 * stage_bytes > 227 * 1024) return AM_OK;
+  int SB = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (SB > 8) SB = 8;
+  a.SB = SB;
+  void* part = nullptr;
+  int rc = workspace(kWsConv, (size_t)a.nslices * a.CO * a.Nv * sizeof(float), &part);
+  if (rc) return rc;
+  a.part = (float*)part;
+  const size_t smem = fixed + (size_t)SB * stage_bytes;
+  AM_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int dbg_env = -1;
+  if (dbg_env < 0) { const char* e = getenv("AM_CONVTC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+  a.dbg = nullptr;
+  if (dbg_env) {
+    void* base = nullptr;
+    if ((rc = workspace(kWsMisc, 64 * sizeof(int) + 1024, &base))) return rc;
+    a.dbg = (long long*)((char*)base + 512);
+    AM_CUDA_TRY(cudaMemsetAsync(a.dbg, 0, 16 * sizeof(long long), st));
+  }
+  conv_wgrad_tc_kernel<<<a.nchunks * a.nslices, 768, smem, st>>>(a);
+  g_launch_count++;
+  AM_CUDA_TRY(cudaGetLastError());
+  if (a.dbg) {
+    long long h[16];
+    AM_CUDA_TRY(cudaMemcpyAsync(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    AM_CUDA_TRY(cudaStreamSynchronize(st));
+    fprintf(stderr, "[wgrad_tc dbg] chunks=%d slices=%d spi=%d SB=%d NP=%d | mma: total %lld wait_tempty %lld wait_full_a %lld wait_full_b %lld | gather0: total %lld wait_raw_full %lld wait_empty_a %lld | loader: total %lld wait_empty_b %lld | acc: total %lld wait_tfull %lld\n",
+            a.nchunks, a.nslices, a.spi, a.SB, a.NP, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10]);
+  }
+  *part_out = a.part;
+  *groups_out = a.nslices;
   *done = true;
   return AM_OK;
 }

@@ -170,4 +170,17 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// 3xTF32 operand split for the kernels that build operands on the fly (gather warps): hi = x rounded to tf32
+// (round-to-nearest, ties away, done on the bit pattern), lo = x - hi exactly (fp32).  lo is handed to the tensor
+// core unrounded: kind::tf32 reads the upper 19 bits of the container, i.e. truncates it, an error of at most
+// 2^-10 |lo| <= 2^-21 |x|, the same order as the lo*lo product 3xTF32 drops anyway.  Non-finite x (or x that rounds
+// up to infinity) travels in hi alone.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const uint32_t hb = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  const float h = __uint_as_float(hb);
+  const bool fin = fabsf(h) < __int_as_float(0x7f800000);
+  hi = fin ? hb : __float_as_uint(x);
+  lo = fin ? __float_as_uint(x - h) : 0u;
+}
+
 }}  // namespace am::ptx

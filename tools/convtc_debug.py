@@ -11,3 +11,5 @@ for xs, ks in [((4096, 1, 28, 28), (20, 1, 5, 5)), ((4096, 20, 12, 12), (50, 20,
         print("fwd", xs, file=sys.stderr); out = am.conv2d(X, W, B); torch.cuda.synchronize()
     print("dgrad", xs, file=sys.stderr)
     am.conv2d_backward(X, W, B, (0, 0), (1, 1), (1, 1), torch.ones_like(out), need_kernel_grad=False); torch.cuda.synchronize()
+    print("wgrad", xs, file=sys.stderr)
+    am.conv2d_backward(X, W, B, (0, 0), (1, 1), (1, 1), torch.ones_like(out), need_input_grad=False); torch.cuda.synchronize()

@@ -6,9 +6,9 @@ the reference's operator interface.  There is no CPU fallback."""
 from . import _capi
 from ._capi import (AmError, F32_AUTO, F32_SIMT, F32_TC, F32_TC_1CTA, F64_AUTO, F64_DMMA, F64_SIMT, set_f32_path,
                     set_f64_path, version)
-from .cuda_tensor import CudaTensor, PackedF32, cuda, cublas_gemm, gemm, gemm_packed, gemm_strided, matmul
+from .cuda_tensor import CudaTensor, PackedF32, cuda, cublas_gemm, gemm, gemm_packed, gemm_packed_bcast, gemm_strided, matmul
 from .nn_primitives import conv2d, conv2d_backward, conv_out_dims
 
-__all__ = ["AmError", "CudaTensor", "cuda", "cublas_gemm", "gemm", "gemm_strided", "gemm_packed", "PackedF32", "matmul", "conv2d",
+__all__ = ["AmError", "CudaTensor", "cuda", "cublas_gemm", "gemm", "gemm_strided", "gemm_packed", "gemm_packed_bcast", "PackedF32", "matmul", "conv2d",
            "conv2d_backward", "conv_out_dims", "set_f32_path", "set_f64_path", "version", "F64_AUTO", "F64_SIMT", "F64_DMMA", "F32_AUTO", "F32_SIMT", "F32_TC",
            "F32_TC_1CTA"]

@@ -22,7 +22,7 @@ CTYPE = {"f32": ctypes.c_float, "f64": ctypes.c_double, "i32": ctypes.c_int32, "
 EXPORTED_SYMBOLS = (
     ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path", "am_set_conv_path",
      "am_cublas_gemm_f32", "am_cublas_gemm_f64", "am_pack_f32_a", "am_pack_f32_b", "am_repack_f32_a",
-     "am_repack_f32_b", "am_gemm_packed_f32", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench"]
+     "am_repack_f32_b", "am_gemm_packed_f32", "am_gemm_packed_f32_bcast", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench"]
     + [f"am_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_host_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_conv2d_forward_{s}" for s in SUFFIXES]
@@ -77,6 +77,7 @@ def lib() -> ctypes.CDLL:
     L.am_repack_f32_a.argtypes = [p, p, p, i64, i64]
     L.am_repack_f32_b.argtypes = [p, p, p, i64, i64]
     L.am_gemm_packed_f32.argtypes = [p, f, p, p, f, p, i64, i64]
+    L.am_gemm_packed_f32_bcast.argtypes = [p, f, p, p, ci, p, i64, i64]
     L.am_packed_free_f32.argtypes = [p]
     for s in ("f32", "f64"):
         ct = CTYPE[s]

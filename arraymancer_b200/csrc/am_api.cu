@@ -300,6 +300,10 @@ int am_gemm_packed_f32(am_stream_t s, float alpha, const am_packed_f32* A, const
                        float* C, int64_t rsC, int64_t csC) {
   return gemm_packed_f32((cudaStream_t)s, alpha, A, B, beta, C, rsC, csC);
 }
+int am_gemm_packed_f32_bcast(am_stream_t s, float alpha, const am_packed_f32* A, const am_packed_f32* B, int npeers,
+                             float* const* peerC, int64_t rsC, int64_t csC) {
+  return gemm_packed_f32_bcast((cudaStream_t)s, alpha, A, B, npeers, peerC, rsC, csC);
+}
 int am_packed_free_f32(am_packed_f32* h) { return packed_free_f32(h); }
 
 // cublas_gemm adapter (cublas.nim:142-170): column-major, op N -> (rs=1, cs=ld), op T -> (rs=ld, cs=1)

@@ -104,6 +104,10 @@ struct TcArgs {
   unsigned* sync_counter;  // grid barrier of the persistent schedule (zeroed before the launch); null = no barrier
   float* C; int64_t rsC, csC;
   float alpha, beta;
+  // fused all-gather: when npeers > 0 the epilogue stores every result element to the same offset of each peer's
+  // copy of C (peer[] holds device pointers mapped over NVLink, this GPU's own copy included) instead of to C
+  int npeers;
+  float* peer[8];
 };
 
 // tile index -> (tm, tn): groups of |group| tiles of one dimension, that dimension fastest inside a group, so that
@@ -310,7 +314,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       tile_coords(p, tile, &tm, &tn);
       const int64_t m = (int64_t)tm * Cfg::TILE_M + (int64_t)cta_rank * 128 + q * 32 + (int)lane;
       const int64_t col0 = (int64_t)tn * Cfg::TILE_N;
-      if (m < p.M) {
+      if (m < p.M && p.npeers > 0) {
+        // GEMM -> all-gather in one kernel: the tile goes straight to every GPU's C (posted stores over NVLink /
+        // NVSwitch; lanes run along C's unit-stride dimension, 128 contiguous bytes per warp store)
+        const int64_t orow = m * p.rsC;
+        const float alpha = p.alpha;
+#pragma unroll
+        for (int i = 0; i < 128; i++) {           // full unroll: acc[] must stay in registers
+          const int64_t n = col0 + half * 128 + i;
+          if (n < p.N) {
+            const float v = epilogue_value<float>(alpha, acc[i], 0.f, 0.f);
+            const int64_t off = orow + n * p.csC;
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+              if (g < p.npeers) p.peer[g][off] = v;
+          }
+        }
+      } else if (m < p.M) {
         float* crow = p.C + m * p.rsC;
         const float alpha = p.alpha, beta = p.beta;
 #pragma unroll
@@ -415,7 +435,7 @@ static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int6
 
 // P rows -> TMEM lanes (C's unit-stride dimension), Q rows -> TMEM columns.
 static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const PackedF32& Q, float alpha,
-                      float beta, float* C, int64_t strideP, int64_t strideQ) {
+                      float beta, float* C, int64_t strideP, int64_t strideQ, int npeers = 0, float* const* peers = nullptr) {
   if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
   static int flush_env = -1;
   if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
@@ -430,6 +450,8 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
   if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 8; }
   args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
+  args.npeers = npeers;
+  for (int g = 0; g < 8; g++) args.peer[g] = (g < npeers) ? peers[g] : nullptr;
   // grid-barrier counter of the persistent schedule: one slot of a small ring, zeroed in stream order
   static int sync_env = -1;
   if (sync_env < 0) { const char* e = getenv("AM_TC_SYNC"); sync_env = (e && e[0] == '0') ? 0 : 1; }
@@ -510,6 +532,17 @@ int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB
   if (!a || !b || !C) { set_last_error("am_gemm_packed_f32: bad argument"); return AM_ERR_INVALID; }
   if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, 2, *a, *b, alpha, beta, C, rsC, csC);
   return run_packed(st, 2, *b, *a, alpha, beta, C, csC, rsC);
+}
+
+// C <- alpha*A*B written to EVERY peer's copy of C (peers[g] = address of C's element (0,0) in GPU g's buffer as
+// mapped into this process, own copy included): the row-sharded GEMM and the all-gather of its result in one kernel.
+int gemm_packed_f32_bcast(cudaStream_t st, float alpha, const void* hA, const void* hB, int npeers, float* const* peers,
+                          int64_t rsC, int64_t csC) {
+  const PackedF32* a = (const PackedF32*)hA; const PackedF32* b = (const PackedF32*)hB;
+  if (!a || !b || !peers || npeers < 1 || npeers > 8) { set_last_error("am_gemm_packed_f32_bcast: bad argument (1..8 peers)"); return AM_ERR_INVALID; }
+  for (int g = 0; g < npeers; g++) if (!peers[g]) { set_last_error("am_gemm_packed_f32_bcast: null peer pointer"); return AM_ERR_INVALID; }
+  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, 2, *a, *b, alpha, 0.f, peers[0], rsC, csC, npeers, peers);
+  return run_packed(st, 2, *b, *a, alpha, 0.f, peers[0], csC, rsC, npeers, peers);
 }
 
 }  // namespace am

@@ -85,6 +85,35 @@ class RowShardedGemm:
         return self.C
 
 
+class SymmetricResult:
+    """The full result matrix C allocated as symmetric memory (torch.distributed._symmetric_memory:
+    one identically-sized allocation per GPU, each mapped into every process of the node over
+    NVLink / NVSwitch).  `peer_ptrs(view)` gives, for a view of this rank's C, the address of the
+    same block in every GPU's copy — what am_gemm_packed_f32_bcast stores to, so the all-gather of
+    SURVEY 8e happens inside the GEMM epilogue instead of as a separate NCCL collective."""
+
+    def __init__(self, shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.C = symm.empty(*shape, dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.C, group)
+        self.world = self.handle.world_size
+        self.rank = self.handle.rank
+        self.bases = [int(x) for x in self.handle.buffer_ptrs]
+        if len(self.bases) != self.world or any(b == 0 for b in self.bases):
+            raise RuntimeError("symmetric memory: peer mapping unavailable")
+        self._base = self.C.data_ptr()
+
+    def peer_ptrs(self, view: torch.Tensor):
+        off = view.data_ptr() - self._base
+        return [b + off for b in self.bases]
+
+    def barrier(self):
+        """Device-side barrier on the current stream across the ranks: afterwards every rank's
+        earlier stores to the peers are complete and visible."""
+        self.handle.barrier()
+
+
 def shard_batch(n_images: int, world: int, rank: int):
     """Contiguous image range of `rank` (the remainder goes to the first ranks)."""
     base, rem = divmod(n_images, world)

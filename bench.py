@@ -137,6 +137,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", default="fused", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = the GEMM epilogue stores C to every GPU's copy over NVLink (symmetric memory); "
+                         "'nccl' = per-chunk ncclAllGather on a second stream")
     ap.add_argument("--verify", action="store_true", help="check the gathered C against a local recomputation of sampled rows of every rank")
     args = ap.parse_args()
     # NCCL prints a version banner on stdout at communicator creation: keep stdout clean for the ONE JSON line
@@ -175,8 +178,29 @@ def main():
     B = torch.rand((n, n), device=dev, dtype=torch.float32, generator=gB) * 2 - 1
     gA = torch.Generator(device=dev); gA.manual_seed(1234 + 7919 * rank)
     A_local = torch.rand((rows_local, n), device=dev, dtype=torch.float32, generator=gA) * 2 - 1
-    C = torch.empty((n, n), device=dev, dtype=torch.float32)          # full result on every rank
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm = args.comm if world > 1 else "none"
+    symC = None
+    if comm == "fused":
+        try:
+            symC = D.SymmetricResult((n, n), torch.float32, dev)
+            C = symC.C
+        except Exception as e:  # no peer mapping on this box: fall back to the NCCL collective, and say so
+            print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using --comm nccl", file=sys.stderr)
+            comm = "nccl"
+            flag = torch.tensor([1], device=dev)
+        else:
+            flag = torch.tensor([0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)                   # all ranks take the same path
+        if int(flag.item()) and comm == "fused":
+            comm, symC = "nccl", None
+    if symC is None:
+        C = torch.empty((n, n), device=dev, dtype=torch.float32)      # full result on every rank
+    if comm == "fused" and args.chunks == 4:
+        chunks = 1                                                    # nothing to overlap: one launch per rank and step
+        mc = D.chunk_rows(n, world, chunks)
+        rows_local = mc * chunks
+        A_local = A_local[:rows_local]
+    comm_stream = torch.cuda.Stream(device=dev) if comm == "nccl" else None
 
     pB = am.PackedF32(B, "b")
     pA = am.PackedF32(A_local[:mc], "a")
@@ -193,10 +217,13 @@ def main():
             if record_kernel:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            am.gemm_packed(1.0, pA, pB, 0.0, mine)            # tcgen05 3xTF32 mainloop
+            if comm == "fused":
+                am.gemm_packed_bcast(1.0, pA, pB, mine, symC.peer_ptrs(mine))   # mainloop + stores to all GPUs
+            else:
+                am.gemm_packed(1.0, pA, pB, 0.0, mine)        # tcgen05 3xTF32 mainloop
             if record_kernel:
                 e1.record(); ev_k0.append(e0); ev_k1.append(e1)
-            if world > 1:
+            if comm == "nccl":
                 span = C[j * world * mc:(j + 1) * world * mc]
                 ready = torch.cuda.Event(); ready.record()
                 with torch.cuda.stream(comm_stream):
@@ -204,8 +231,10 @@ def main():
                     works.append(dist.all_gather_into_tensor(span, mine, async_op=True))
         for w in works:
             w.wait()
-        if world > 1:
+        if comm == "nccl":
             torch.cuda.current_stream().wait_stream(comm_stream)
+        if comm == "fused":
+            symC.barrier()                                    # every rank's tiles have landed in every copy of C
 
     def barrier():
         if world > 1:
@@ -309,9 +338,13 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"row-sharded SGEMM {n}x{n}x{n}, 3xTF32 on tcgen05 (BASELINE configs[4])",
                    "M": n, "N": n, "K": n, "parallelism": f"rows of A block-cyclic over {world} GPU(s), B replicated, "
-                   f"C all-gathered over NCCL ({chunks} chunk(s)/rank, overlapped)",
+                   + {"fused": "C tiles stored to every GPU's copy by the GEMM epilogue (symmetric memory over NVLink, no separate collective)",
+                      "nccl": f"C all-gathered over NCCL ({chunks} chunk(s)/rank, overlapped)",
+                      "none": "single GPU"}[comm],
+                   "comm": comm, "chunks": chunks,
                    "l2": "operands 4 GiB each >> 126 MB L2 (no flush needed)",
-                   "timed": "split/pack of A rows and B + tcgen05 mainloop + all-gather of C"},
+                   "timed": "split/pack of A rows and B + tcgen05 mainloop + " +
+                            ("stores of C to all GPUs + cross-GPU barrier" if comm == "fused" else "all-gather of C")},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "kernel": "gemm_tf32x3_kernel<2>", "kernel_ms": kern_ms, "flops_per_launch": kern_flops,

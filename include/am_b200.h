@@ -104,6 +104,15 @@ AM_API int am_repack_f32_b(am_stream_t stream, am_packed_f32* h, const float* B,
 AM_API int am_gemm_packed_f32(am_stream_t stream, float alpha, const am_packed_f32* A,
                               const am_packed_f32* B, float beta, float* C, int64_t rowStrideC,
                               int64_t colStrideC);
+/* Row-sharded GEMM fused with the all-gather of its result ("rank r owns rows of A and of C ...
+ * ncclAllGather of C"): C <- alpha*A*B is stored by the GEMM epilogue to the same offsets of EVERY GPU's copy
+ * of C.  peerC[g] = device address, valid in the calling process (peer-mapped / symmetric memory over NVLink),
+ * of element (0,0) of the output block in GPU g's buffer; the caller's own copy is one of the entries.
+ * beta is 0 by construction (remote copies are write-only).  1 <= npeers <= 8.  The caller synchronises the
+ * GPUs (stream order + a cross-GPU barrier) before any of them reads C. */
+AM_API int am_gemm_packed_f32_bcast(am_stream_t stream, float alpha, const am_packed_f32* A,
+                                    const am_packed_f32* B, int npeers, float* const* peerC,
+                                    int64_t rowStrideC, int64_t colStrideC);
 AM_API int am_packed_free_f32(am_packed_f32* h);
 
 /* ---- cuBLAS-shaped adapter -------------------------------------------------------------

@@ -68,6 +68,68 @@ split_pack_kernel(const float* __restrict__ X, int64_t R, int64_t K, int64_t r_s
   }
 }
 
+// Vector variant for the common case (unit stride along one source dimension, the other stride and the extents
+// multiples of 4, 16-byte aligned base): 64 x 64 tiles, 128-bit loads along the contiguous source dimension and
+// 128-bit stores along k.  The scalar kernel above moved 2.2 TB/s on a 32768^2 operand (5.8 ms of every sharded step).
+__device__ __forceinline__ void split4(const float4 x, float4* h, float4* l) {
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  float hs[4], ls[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float v = xs[e];
+    float hh = v, ll = 0.f;
+    if (isfinite(v)) { hh = ptx::to_tf32_rna(v); ll = ptx::to_tf32_rna(v - hh); if (!isfinite(hh)) { hh = v; ll = 0.f; } }
+    hs[e] = hh; ls[e] = ll;
+  }
+  *h = make_float4(hs[0], hs[1], hs[2], hs[3]);
+  *l = make_float4(ls[0], ls[1], ls[2], ls[3]);
+}
+
+__global__ void __launch_bounds__(256)
+split_pack_vec_kernel(const float* __restrict__ X, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride,
+                      float* __restrict__ hi, float* __restrict__ lo, int64_t Kpad, int k_fast) {
+  __shared__ float tile[64][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16
+  const int64_t k0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  if (k_fast) {                                               // k contiguous in the source: straight through
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = r0 + ty + 16 * i, k = k0 + 4 * tx;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R && k < K) x = __ldg(reinterpret_cast<const float4*>(X + r * r_stride + k));
+      float4 h, l;
+      split4(x, &h, &l);
+      if (k < Kpad) {
+        *reinterpret_cast<float4*>(hi + r * Kpad + k) = h;
+        *reinterpret_cast<float4*>(lo + r * Kpad + k) = l;
+      }
+    }
+    return;
+  }
+  // rows contiguous in the source: read 128-bit pieces along r, transpose through shared memory
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int64_t r = r0 + 4 * tx, k = k0 + ty + 16 * i;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R && k < K) x = __ldg(reinterpret_cast<const float4*>(X + k * k_stride + r));
+    tile[ty + 16 * i][4 * tx + 0] = x.x; tile[ty + 16 * i][4 * tx + 1] = x.y;
+    tile[ty + 16 * i][4 * tx + 2] = x.z; tile[ty + 16 * i][4 * tx + 3] = x.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int rl = ty + 16 * i;
+    const int64_t r = r0 + rl, k = k0 + 4 * tx;
+    const float4 x = make_float4(tile[4 * tx + 0][rl], tile[4 * tx + 1][rl], tile[4 * tx + 2][rl], tile[4 * tx + 3][rl]);
+    float4 h, l;
+    split4(x, &h, &l);
+    if (k < Kpad) {
+      *reinterpret_cast<float4*>(hi + r * Kpad + k) = h;
+      *reinterpret_cast<float4*>(lo + r * Kpad + k) = l;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ mainloop
 // Why the accumulators live in REGISTERS, not only in TMEM: the tensor core adds each MMA result
 // into its fp32 accumulator with truncation, a bias that grows linearly with the length of the
@@ -426,6 +488,18 @@ static int64_t pad_k(int64_t k) { return round_up(k, 32); }
 static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride,
                      PackedF32* out) {
   if (out->Rpad / 32 > 65535) { set_last_error("gemm_f32_tc: dimension too large for the pack grid"); return AM_ERR_INVALID; }
+  const bool kf = iabs64(k_stride) <= iabs64(r_stride);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && R % 4 == 0 && K % 4 == 0 && out->Rpad % 64 == 0 &&
+                      (kf ? (k_stride == 1 && r_stride % 4 == 0) : (r_stride == 1 && k_stride % 4 == 0));
+  static const bool no_vec = getenv("AM_PACK_SCALAR") != nullptr;
+  if (vec_ok && !no_vec) {
+    // rows r >= R (padding) are produced as zeros by the bounds test; k in [K, Kpad) likewise (Kpad - K < 32, K % 4 == 0)
+    split_pack_vec_kernel<<<dim3((unsigned)ceil_div(out->Kpad, 64), (unsigned)(out->Rpad / 64)), 256, 0, st>>>(
+        X, R, K, r_stride, k_stride, out->hi, out->lo, out->Kpad, kf ? 1 : 0);
+    g_launch_count++;
+    AM_CUDA_TRY(cudaGetLastError());
+    return AM_OK;
+  }
   split_pack_kernel<<<dim3((unsigned)(out->Kpad / 32), (unsigned)(out->Rpad / 32)), 256, 0, st>>>(
       X, R, K, r_stride, k_stride, out->hi, out->lo, out->Kpad, iabs64(k_stride) <= iabs64(r_stride));
   g_launch_count++;

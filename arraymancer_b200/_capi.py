@@ -77,7 +77,7 @@ def lib() -> ctypes.CDLL:
     L.am_repack_f32_a.argtypes = [p, p, p, i64, i64]
     L.am_repack_f32_b.argtypes = [p, p, p, i64, i64]
     L.am_gemm_packed_f32.argtypes = [p, f, p, p, f, p, i64, i64]
-    L.am_gemm_packed_f32_bcast.argtypes = [p, f, p, p, ci, p, i64, i64]
+    L.am_gemm_packed_f32_bcast.argtypes = [p, f, p, p, ci, p, ci, i64, i64]
     L.am_packed_free_f32.argtypes = [p]
     for s in ("f32", "f64"):
         ct = CTYPE[s]

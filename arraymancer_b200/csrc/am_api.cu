@@ -301,8 +301,8 @@ int am_gemm_packed_f32(am_stream_t s, float alpha, const am_packed_f32* A, const
   return gemm_packed_f32((cudaStream_t)s, alpha, A, B, beta, C, rsC, csC);
 }
 int am_gemm_packed_f32_bcast(am_stream_t s, float alpha, const am_packed_f32* A, const am_packed_f32* B, int npeers,
-                             float* const* peerC, int64_t rsC, int64_t csC) {
-  return gemm_packed_f32_bcast((cudaStream_t)s, alpha, A, B, npeers, peerC, rsC, csC);
+                             float* const* peerC, int self_index, int64_t rsC, int64_t csC) {
+  return gemm_packed_f32_bcast((cudaStream_t)s, alpha, A, B, npeers, peerC, self_index, rsC, csC);
 }
 int am_packed_free_f32(am_packed_f32* h) { return packed_free_f32(h); }
 

@@ -28,7 +28,7 @@ int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_st
 int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride);
 int packed_free_f32(void* handle);
 int gemm_packed_f32_bcast(cudaStream_t st, float alpha, const void* hA, const void* hB, int npeers, float* const* peers,
-                          int64_t rsC, int64_t csC);
+                          int self, int64_t rsC, int64_t csC);
 int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB, float beta, float* C, int64_t rsC,
                     int64_t csC);
 

@@ -169,6 +169,7 @@ struct TcArgs {
   // fused all-gather: when npeers > 0 the epilogue stores every result element to the same offset of each peer's
   // copy of C (peer[] holds device pointers mapped over NVLink, this GPU's own copy included) instead of to C
   int npeers;
+  int self;                // which peer[] entry is this GPU's own copy
   float* peer[8];
 };
 
@@ -348,12 +349,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * 128u;
     const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     uint32_t chain = 0;
+    // fused all-gather: a finished tile is stored to the LOCAL copy of C in the epilogue; its copies to the peers are
+    // trickled out between the chain drains of the NEXT tile (this thread re-reads its own row from L2 and posts it to
+    // the 7 peers, a few elements per chain).  Storing all 8 copies in the epilogue made every CTA burst ~1 MB onto
+    // NVLink at the same moment (the per-wave grid barrier keeps the CTAs in lockstep) and cost 21 % at 8 GPUs.
+    const float* fwd_src = nullptr;               // this thread's row segment of the previous tile (local copy)
+    int64_t fwd_off = 0;                          // its offset inside C (same in every copy)
+    int fwd_n = 0, fwd_pos = 0;                   // valid columns / columns already forwarded
+    auto forward = [&](int count) {
+      for (int e = 0; e < count && fwd_pos < fwd_n; e++, fwd_pos++) {
+        const int64_t o = fwd_off + (int64_t)fwd_pos * p.csC;
+        const float v = fwd_src[(int64_t)fwd_pos * p.csC];
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+          if (g < p.npeers && g != p.self) p.peer[g][o] = v;
+      }
+    };
     for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; i++) acc[i] = 0.f;
       for (int c = 0; c < nchains; c++, chain++) {
         const int buf = chain & 1;
+        if (p.npeers > 1) forward((int)(((int64_t)(c + 1) * 128 + nchains - 1) / nchains) - fwd_pos);   // evenly over the tile
         ptx::mbar_wait(tfull_bar(buf), (chain >> 1) & 1u);
         ptx::tc_fence_after();
 #pragma unroll
@@ -376,21 +394,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       tile_coords(p, tile, &tm, &tn);
       const int64_t m = (int64_t)tm * Cfg::TILE_M + (int64_t)cta_rank * 128 + q * 32 + (int)lane;
       const int64_t col0 = (int64_t)tn * Cfg::TILE_N;
-      if (m < p.M && p.npeers > 0) {
-        // GEMM -> all-gather in one kernel: the tile goes straight to every GPU's C (posted stores over NVLink /
-        // NVSwitch; lanes run along C's unit-stride dimension, 128 contiguous bytes per warp store)
-        const int64_t orow = m * p.rsC;
-        const float alpha = p.alpha;
+      if (p.npeers > 0) {
+        // GEMM -> all-gather in one kernel: this tile to the local copy now, to the peers during the next tile
+        forward(128);                              // whatever is left of the previous tile
+        fwd_n = 0; fwd_pos = 0;
+        if (m < p.M) {
+          const int64_t n0 = col0 + half * 128;
+          const int64_t orow = m * p.rsC + n0 * p.csC;
+          float* crow = p.peer[p.self] + orow;
+          const float alpha = p.alpha;
+          int nvalid = 0;
 #pragma unroll
-        for (int i = 0; i < 128; i++) {           // full unroll: acc[] must stay in registers
-          const int64_t n = col0 + half * 128 + i;
-          if (n < p.N) {
-            const float v = epilogue_value<float>(alpha, acc[i], 0.f, 0.f);
-            const int64_t off = orow + n * p.csC;
-#pragma unroll
-            for (int g = 0; g < 8; g++)
-              if (g < p.npeers) p.peer[g][off] = v;
+          for (int i = 0; i < 128; i++) {           // full unroll: acc[] must stay in registers
+            if (n0 + i < p.N) { crow[i * p.csC] = epilogue_value<float>(alpha, acc[i], 0.f, 0.f); nvalid = i + 1; }
           }
+          fwd_src = crow; fwd_off = orow; fwd_n = nvalid;
         }
       } else if (m < p.M) {
         float* crow = p.C + m * p.rsC;
@@ -406,6 +424,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
         }
       }
     }
+    if (p.npeers > 1) forward(128);                // the last tile's copies
   }
 
   // teardown: nobody may leave (or free TMEM) while the pair still has traffic in flight
@@ -509,7 +528,8 @@ static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int6
 
 // P rows -> TMEM lanes (C's unit-stride dimension), Q rows -> TMEM columns.
 static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const PackedF32& Q, float alpha,
-                      float beta, float* C, int64_t strideP, int64_t strideQ, int npeers = 0, float* const* peers = nullptr) {
+                      float beta, float* C, int64_t strideP, int64_t strideQ, int npeers = 0, float* const* peers = nullptr,
+                      int self = 0) {
   if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
   static int flush_env = -1;
   if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
@@ -524,7 +544,7 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
   if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 8; }
   args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
-  args.npeers = npeers;
+  args.npeers = npeers; args.self = self;
   for (int g = 0; g < 8; g++) args.peer[g] = (g < npeers) ? peers[g] : nullptr;
   // grid-barrier counter of the persistent schedule: one slot of a small ring, zeroed in stream order
   static int sync_env = -1;
@@ -611,12 +631,12 @@ int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB
 // C <- alpha*A*B written to EVERY peer's copy of C (peers[g] = address of C's element (0,0) in GPU g's buffer as
 // mapped into this process, own copy included): the row-sharded GEMM and the all-gather of its result in one kernel.
 int gemm_packed_f32_bcast(cudaStream_t st, float alpha, const void* hA, const void* hB, int npeers, float* const* peers,
-                          int64_t rsC, int64_t csC) {
+                          int self, int64_t rsC, int64_t csC) {
   const PackedF32* a = (const PackedF32*)hA; const PackedF32* b = (const PackedF32*)hB;
-  if (!a || !b || !peers || npeers < 1 || npeers > 8) { set_last_error("am_gemm_packed_f32_bcast: bad argument (1..8 peers)"); return AM_ERR_INVALID; }
+  if (!a || !b || !peers || npeers < 1 || npeers > 8 || self < 0 || self >= npeers) { set_last_error("am_gemm_packed_f32_bcast: bad argument (1..8 peers)"); return AM_ERR_INVALID; }
   for (int g = 0; g < npeers; g++) if (!peers[g]) { set_last_error("am_gemm_packed_f32_bcast: null peer pointer"); return AM_ERR_INVALID; }
-  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, 2, *a, *b, alpha, 0.f, peers[0], rsC, csC, npeers, peers);
-  return run_packed(st, 2, *b, *a, alpha, 0.f, peers[0], csC, rsC, npeers, peers);
+  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, 2, *a, *b, alpha, 0.f, peers[self], rsC, csC, npeers, peers, self);
+  return run_packed(st, 2, *b, *a, alpha, 0.f, peers[self], csC, rsC, npeers, peers, self);
 }
 
 }  // namespace am

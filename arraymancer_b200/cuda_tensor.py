@@ -251,11 +251,11 @@ class PackedF32:
             pass
 
 
-def gemm_packed_bcast(alpha: float, A: PackedF32, B: PackedF32, C_view: torch.Tensor, peer_ptrs) -> torch.Tensor:
+def gemm_packed_bcast(alpha: float, A: PackedF32, B: PackedF32, C_view: torch.Tensor, peer_ptrs, self_index: int) -> torch.Tensor:
     """C_view <- alpha*A*B, stored by the GEMM epilogue to the same block of EVERY GPU's copy of C
     (row-sharded GEMM fused with the all-gather of its result).  `peer_ptrs[g]` is the
     address, mapped into this process (symmetric / peer memory), of C_view's first element in GPU
-    g's buffer; this GPU's own address is one of them.  The caller orders the GPUs (stream order +
+    g's buffer; `peer_ptrs[self_index]` is this GPU's own address (== C_view.data_ptr()).  The caller orders the GPUs (stream order +
     a cross-GPU barrier) before any of them reads C."""
     if A.role != "a" or B.role != "b" or A.shape[1] != B.shape[0] or tuple(C_view.shape) != (A.shape[0], B.shape[1]):
         raise IndexError("gemm_packed_bcast: operand roles / shapes do not match")
@@ -264,7 +264,7 @@ def gemm_packed_bcast(alpha: float, A: PackedF32, B: PackedF32, C_view: torch.Te
         raise ValueError("gemm_packed_bcast: 1..8 peers")
     arr = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(x)) for x in peer_ptrs])
     with torch.cuda.device(C_view.device):
-        _capi.check(_capi.lib().am_gemm_packed_f32_bcast(_stream_ptr(C_view), alpha, A._h, B._h, n, arr,
+        _capi.check(_capi.lib().am_gemm_packed_f32_bcast(_stream_ptr(C_view), alpha, A._h, B._h, n, arr, int(self_index),
                                                          C_view.stride(0), C_view.stride(1)))
     return C_view
 

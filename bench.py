@@ -218,7 +218,7 @@ def main():
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             if comm == "fused":
-                am.gemm_packed_bcast(1.0, pA, pB, mine, symC.peer_ptrs(mine))   # mainloop + stores to all GPUs
+                am.gemm_packed_bcast(1.0, pA, pB, mine, symC.peer_ptrs(mine), symC.rank)   # mainloop + stores to all GPUs
             else:
                 am.gemm_packed(1.0, pA, pB, 0.0, mine)        # tcgen05 3xTF32 mainloop
             if record_kernel:

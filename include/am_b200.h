@@ -107,12 +107,14 @@ AM_API int am_gemm_packed_f32(am_stream_t stream, float alpha, const am_packed_f
 /* Row-sharded GEMM fused with the all-gather of its result ("rank r owns rows of A and of C ...
  * ncclAllGather of C"): C <- alpha*A*B is stored by the GEMM epilogue to the same offsets of EVERY GPU's copy
  * of C.  peerC[g] = device address, valid in the calling process (peer-mapped / symmetric memory over NVLink),
- * of element (0,0) of the output block in GPU g's buffer; the caller's own copy is one of the entries.
+ * of element (0,0) of the output block in GPU g's buffer; peerC[self_index] is the caller's own copy (written in
+ * the tile epilogue; the copies to the peers are re-read from it and posted between the accumulation chains of the
+ * following tile, so the NVLink traffic is spread over the mainloop instead of bursting).
  * beta is 0 by construction (remote copies are write-only).  1 <= npeers <= 8.  The caller synchronises the
  * GPUs (stream order + a cross-GPU barrier) before any of them reads C. */
 AM_API int am_gemm_packed_f32_bcast(am_stream_t stream, float alpha, const am_packed_f32* A,
                                     const am_packed_f32* B, int npeers, float* const* peerC,
-                                    int64_t rowStrideC, int64_t colStrideC);
+                                    int self_index, int64_t rowStrideC, int64_t colStrideC);
 AM_API int am_packed_free_f32(am_packed_f32* h);
 
 /* ---- cuBLAS-shaped adapter -------------------------------------------------------------
@@ -143,13 +145,14 @@ typedef struct am_conv2d_desc {
 
 AM_API int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo);
 /* Conv kernel selector (process-wide, default AM_CONV_AUTO):
- * AUTO   = float32: shared-memory-staged direct SIMT kernels (forward / stride-1 dgrad / wgrad, kW in {1,3,5,7},
- *          dilation 1) when the tiles fit, generic gather kernels otherwise; other dtypes: generic gather kernels;
+ * AUTO   = float32: per call the family that measured fastest for the shape — tcgen05 kernels (forward when
+ *          Cout >= 32 and C*kH*kW >= 128; GEMM + col2im data gradient for single-tile images; weight gradient
+ *          whenever it fits: Cout <= 64), else the direct SIMT kernels, else the generic gather kernels;
+ *          other dtypes: generic gather kernels (bit-exact integers);
  * GATHER = generic implicit-GEMM gather kernels everywhere (fallback / comparison);
- * DIRECT = same as AUTO (kept for symmetry with the test matrix);
- * TC     = float32 forward / stride-1 dgrad on the tcgen05 implicit-GEMM kernel (Cout <= 64) — correct and tested,
- *          but its per-element global gather is latency-bound (measured slower than DIRECT on the LeNet layers,
- *          profiles/r01_bringup.md), so it is opt-in. */
+ * DIRECT = float32 direct SIMT kernels where they apply (stride-1, dilation-1, kW in {1,3,5,7}), no tensor cores;
+ * TC     = float32 tcgen05 kernels wherever they fit (Cout <= 64, ...), then DIRECT, then GATHER.
+ * Every family is deterministic and is run over the whole parity matrix (tests/test_gpu_conv.py). */
 enum { AM_CONV_AUTO = 0, AM_CONV_GATHER = 1, AM_CONV_DIRECT = 2, AM_CONV_TC = 3 };
 AM_API int am_set_conv_path(int path);
 

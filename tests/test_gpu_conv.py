@@ -92,15 +92,20 @@ CASES = [  # input, kernel, padding, stride, dilation
     ((3, 5, 40, 37), (9, 5, 3, 3), (1, 1), (1, 1), (1, 1)),        # several row bands / images per CTA
     ((2, 3, 9, 9), (4, 3, 3, 3), (3, 3), (1, 1), (1, 1)),          # padding larger than the kernel reach
     ((70, 2, 6, 6), (3, 2, 3, 3), (1, 1), (1, 1), (1, 1)),         # many small images per CTA
+    ((5, 20, 12, 12), (50, 20, 5, 5), (0, 0), (1, 1), (1, 1)),     # cv2 with an odd batch: partial image group / slices
+    ((3, 6, 8, 8), (64, 6, 3, 3), (1, 1), (1, 1), (1, 1)),         # 64 output channels: full tensor-core N, padded taps
+    ((2, 40, 10, 10), (33, 40, 3, 3), (0, 0), (1, 1), (1, 1)),     # 360 GEMM rows: several 128-row chunks
+    ((4, 8, 9, 9), (16, 8, 2, 2), (0, 1), (1, 2), (1, 1)),         # even kernel, mixed stride, one-sided reach
 ]
 
 
-@pytest.fixture(params=["auto", "tc", "gather"])
+@pytest.fixture(params=["auto", "tc", "direct", "gather"])
 def conv_path(request, am):
-    """All three kernel families: smem-staged direct SIMT kernels (AUTO), tcgen05 implicit GEMM (TC, opt-in) and the
-    generic gather kernels (GATHER, the fallback)."""
+    """Every kernel family over the whole matrix: AUTO (per-shape pick), the tcgen05 kernels wherever they fit (TC),
+    the smem-staged direct SIMT kernels (DIRECT) and the generic gather kernels (GATHER, the fallback)."""
     from arraymancer_b200 import _capi
-    _capi.set_conv_path({"auto": _capi.CONV_AUTO, "tc": _capi.CONV_TC, "gather": _capi.CONV_GATHER}[request.param])
+    _capi.set_conv_path({"auto": _capi.CONV_AUTO, "tc": _capi.CONV_TC, "direct": _capi.CONV_DIRECT,
+                         "gather": _capi.CONV_GATHER}[request.param])
     yield request.param
     _capi.set_conv_path(_capi.CONV_AUTO)
 

@@ -354,6 +354,37 @@ DEF_CONV(f64, double)
 DEF_CONV(i32, int32_t)
 DEF_CONV(i64, int64_t)
 
+#define DEF_NN(SUF, T)                                                                                         \
+  int am_relu_forward_##SUF(am_stream_t s, int64_t n, const T* x, T* y) { return relu_forward<T>((cudaStream_t)s, n, x, y); } \
+  int am_relu_backward_##SUF(am_stream_t s, int64_t n, const T* g, const T* c, T* o) {                          \
+    return relu_backward<T>((cudaStream_t)s, n, g, c, o);                                                      \
+  }                                                                                                            \
+  int am_maxpool2d_forward_##SUF(am_stream_t s, int64_t N, int64_t C, int64_t H, int64_t W, int64_t kH, int64_t kW, \
+                                 int64_t pH, int64_t pW, int64_t sH, int64_t sW, const T* x, T* y, int64_t* idx) { \
+    return maxpool2d_forward<T>((cudaStream_t)s, N, C, H, W, kH, kW, pH, pW, sH, sW, x, y, idx);               \
+  }                                                                                                            \
+  int am_maxpool2d_backward_##SUF(am_stream_t s, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, T* gi, \
+                                  int overlap) {                                                               \
+    return maxpool2d_backward<T>((cudaStream_t)s, n_in, n_out, idx, go, gi, overlap);                          \
+  }                                                                                                            \
+  int am_linear_forward_##SUF(am_stream_t s, int64_t b, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y) { \
+    return linear_forward<T>((cudaStream_t)s, b, in, out, x, w, bias, y);                                      \
+  }                                                                                                            \
+  int am_linear_backward_##SUF(am_stream_t s, int64_t b, int64_t in, int64_t out, const T* x, const T* w, const T* go, \
+                               T* gi, T* gw, T* gb) {                                                          \
+    return linear_backward<T>((cudaStream_t)s, b, in, out, x, w, go, gi, gw, gb);                              \
+  }                                                                                                            \
+  int am_sparse_softmax_cross_entropy_##SUF(am_stream_t s, int64_t b, int64_t f, const T* x, int64_t rs, int64_t cs, \
+                                            const int64_t* labels, T* loss) {                                  \
+    return ssce_forward<T>((cudaStream_t)s, b, f, x, rs, cs, labels, loss);                                    \
+  }                                                                                                            \
+  int am_sparse_softmax_cross_entropy_backward_##SUF(am_stream_t s, int64_t b, int64_t f, T grad, const T* x, int64_t rs, \
+                                                     int64_t cs, const int64_t* labels, T* out) {              \
+    return ssce_backward<T>((cudaStream_t)s, b, f, grad, x, rs, cs, labels, out);                              \
+  }
+DEF_NN(f32, float)
+DEF_NN(f64, double)
+
 #define DEF_HOST(SUF, T)                                                                                       \
   int am_host_gemm_strided_##SUF(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA, \
                                  const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) { \

@@ -45,6 +45,26 @@ template <class T>
 int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel,
                     const T* grad_output, T* grad_input, T* grad_kernel, T* grad_bias);
 
+// nn_ops.cu — ReLU, MaxPool2D, linear-layer bias passes, sparse softmax cross-entropy
+template <class T> int relu_forward(cudaStream_t st, int64_t n, const T* x, T* y);
+template <class T> int relu_backward(cudaStream_t st, int64_t n, const T* grad, const T* cached, T* out);
+template <class T>
+int maxpool2d_forward(cudaStream_t st, int64_t N, int64_t C, int64_t H, int64_t W, int64_t kH, int64_t kW, int64_t padH,
+                      int64_t padW, int64_t sH, int64_t sW, const T* x, T* y, int64_t* idx);
+template <class T>
+int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, T* gi, int windows_overlap);
+template <class T>
+int linear_forward(cudaStream_t st, int64_t batch, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y);
+template <class T>
+int linear_backward(cudaStream_t st, int64_t batch, int64_t in, int64_t out, const T* x, const T* w, const T* go, T* gi,
+                    T* gw, T* gb);
+template <class T>
+int ssce_forward(cudaStream_t st, int64_t batch, int64_t features, const T* x, int64_t rs, int64_t cs, const int64_t* labels,
+                 T* loss_dev);
+template <class T>
+int ssce_backward(cudaStream_t st, int64_t batch, int64_t features, T grad, const T* x, int64_t rs, int64_t cs,
+                  const int64_t* labels, T* out);
+
 // peaks.cu
 int microbench(int which, double* tops);
 

@@ -188,6 +188,43 @@ AM_API int am_host_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alp
                                     int64_t rsA, int64_t csA, const int64_t* B, int64_t rsB,
                                     int64_t csB, int64_t beta, int64_t* C, int64_t rsC, int64_t csC);
 
+/* ---- LeNet companions: the HBM-bound operators between the contractions ------------
+ * so that a forward + backward step of the reference's ex02_mnist network stays on the device.  Dense NCHW /
+ * row-major device buffers, outputs pre-allocated by the caller, asynchronous on `stream`, deterministic.
+ *   relu / relu_backward             nn_primitives/nnp_activation.nim:35-36, 65-70  (max(0,x); cached <= 0 ? 0 : g)
+ *   maxpool2d / maxpool2d_backward   nn_primitives/nnp_maxpooling.nim:19-83  (max_indices = flat input index, int64;
+ *                                    first maximum wins; backward ASSIGNS grad_out[i] to grad_in[max_indices[i]],
+ *                                    the last i wins where windows overlap: pass windows_overlap = 1 unless
+ *                                    stride >= kernel in both dimensions)
+ *   linear / linear_backward         nn_primitives/nnp_linear.nim:20-66  (y = x*W^T + b; gI = gO*W, gW = gO^T*x,
+ *                                    gB = sum(gO, axis 0); bias / any gradient pointer may be NULL)
+ *   sparse_softmax_cross_entropy     nn_primitives/nnp_softmax_cross_entropy.nim:100-178 (mean over the batch of
+ *   (+ _backward)                    logsumexp(x_i) - x_i[label_i], streaming max / sum-exp per row; the scalar loss
+ *                                    is written to device memory) and :219-252 (grad*(softmax - onehot)/batch). */
+#define AM_DECL_NN(SUF, T)                                                                                 \
+  AM_API int am_relu_forward_##SUF(am_stream_t stream, int64_t n, const T* x, T* y);                         \
+  AM_API int am_relu_backward_##SUF(am_stream_t stream, int64_t n, const T* gradient, const T* cached, T* out); \
+  AM_API int am_maxpool2d_forward_##SUF(am_stream_t stream, int64_t N, int64_t C, int64_t H, int64_t W, int64_t kH, \
+                                        int64_t kW, int64_t padH, int64_t padW, int64_t strideH, int64_t strideW,  \
+                                        const T* input, T* maxpooled, int64_t* max_indices);                 \
+  AM_API int am_maxpool2d_backward_##SUF(am_stream_t stream, int64_t n_input, int64_t n_output,              \
+                                         const int64_t* max_indices, const T* grad_output, T* grad_input,    \
+                                         int windows_overlap);                                               \
+  AM_API int am_linear_forward_##SUF(am_stream_t stream, int64_t batch, int64_t in_features, int64_t out_features, \
+                                     const T* input, const T* weight, const T* bias, T* output);             \
+  AM_API int am_linear_backward_##SUF(am_stream_t stream, int64_t batch, int64_t in_features, int64_t out_features, \
+                                      const T* input, const T* weight, const T* grad_output, T* grad_input,  \
+                                      T* grad_weight, T* grad_bias);                                         \
+  AM_API int am_sparse_softmax_cross_entropy_##SUF(am_stream_t stream, int64_t batch, int64_t features,      \
+                                                   const T* input, int64_t rowStride, int64_t colStride,     \
+                                                   const int64_t* labels, T* loss_device);                   \
+  AM_API int am_sparse_softmax_cross_entropy_backward_##SUF(am_stream_t stream, int64_t batch, int64_t features, \
+                                                            T gradient, const T* cached_input, int64_t rowStride, \
+                                                            int64_t colStride, const int64_t* labels, T* grad_input);
+AM_DECL_NN(f32, float)
+AM_DECL_NN(f64, double)
+#undef AM_DECL_NN
+
 /* ---- measurement helpers (bench.py / profiles) -------------------------------------------
  * Number of kernels this library has launched on the calling process since load. */
 AM_API int64_t am_kernel_launch_count(void);

@@ -112,3 +112,20 @@ if __name__ == "__main__":
     with open(out, "w") as f:
         json.dump(ALL, f, indent=1)
     print("wrote", out)
+
+
+# ---- the reference's own vectors for the operators around the contractions
+# tests/nn_primitives/test_nnp_maxpool.nim:21-32  (kernel (2,2), padding (0,0), stride (2,2))
+MAXPOOL = {
+    "input": [[1, 1, 2, 4], [5, 6, 7, 8], [3, 2, 1, 0], [1, 2, 3, 4]],      # reshape(1,1,4,4)
+    "kernel": (2, 2), "padding": (0, 0), "stride": (2, 2),
+    "maxpooled": [6, 8, 3, 4],                                              # reshape(1,1,2,2)
+    "max_indices": [5, 7, 8, 15],
+}
+# tests/nn_primitives/test_nnp_loss.nim:29-44  (`~=` is |a - b| <= 2e-5)
+SOFTMAX_CE = {
+    "predicted": [[-3.44, 1.16, -0.81, 3.91]],
+    "sparse_truth": [3],
+    "loss": 0.0709, "tol": 2e-5,
+    "grad_mre_tol": 1e-6,           # analytic backward vs loss * numerical_gradient, :57-60
+}

@@ -1,0 +1,209 @@
+"""GPU parity tests of the LeNet companions (relu, maxpool2d, linear, sparse softmax
+cross-entropy), through the C-ABI, against the numpy oracle (oracle/nn_oracle.py) and the reference's own vectors
+(tests/nn_primitives/test_nnp_maxpool.nim, test_nnp_loss.nim), plus a device-resident LeNet forward + backward step."""
+import numpy as np
+import pytest
+
+from oracle import nn_oracle as O
+from tests.golden import known_answers as KA
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+NP = {"f32": np.float32, "f64": np.float64}
+
+
+@pytest.fixture(scope="module")
+def am():
+    import arraymancer_b200 as am
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return am
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(g, r):
+    g = np.asarray(g, np.float64); r = np.asarray(r, np.float64)
+    return np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-300)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+@pytest.mark.parametrize("n", [0, 1, 5, 1024, 4099])
+def test_relu_bit_exact(am, dt, n):
+    rng = np.random.default_rng(n)
+    x = (rng.random(n) * 2 - 1).astype(NP[dt])
+    if n >= 5:
+        x[0] = 0.0; x[1] = -0.0; x[2] = np.nan; x[3] = np.inf; x[4] = -np.inf
+    g = (rng.random(n) * 2 - 1).astype(NP[dt])
+    y = am.relu(dev(x)).cpu().numpy()
+    assert np.array_equal(y, O.relu(x), equal_nan=True)
+    gb = am.relu_backward(dev(g), dev(x)).cpu().numpy()
+    assert np.array_equal(gb, O.relu_backward(g, x), equal_nan=True)
+
+
+def test_maxpool_reference_vectors(am):
+    c = KA.MAXPOOL
+    a = np.array(c["input"], dtype=np.float32).reshape(1, 1, 4, 4)
+    idx, pooled = am.maxpool2d(dev(a), c["kernel"], c["padding"], c["stride"])
+    assert pooled.cpu().numpy().reshape(-1).tolist() == c["maxpooled"]
+    assert idx.cpu().numpy().tolist() == c["max_indices"]
+    grad = am.maxpool2d_backward(a.shape, idx, pooled).cpu().numpy()
+    want = np.zeros(16, np.float32); want[c["max_indices"]] = c["maxpooled"]
+    assert np.array_equal(grad.reshape(-1), want)
+
+
+POOL_CASES = [  # input shape, kernel, padding, stride
+    ((3, 20, 24, 24), (2, 2), (0, 0), (2, 2)),      # LeNet pool 1
+    ((3, 50, 8, 8), (2, 2), (0, 0), (2, 2)),        # LeNet pool 2
+    ((2, 3, 7, 9), (3, 3), (1, 1), (2, 2)),         # overlapping windows + padding
+    ((2, 2, 5, 5), (3, 2), (1, 0), (1, 1)),         # stride 1: heavy overlap
+    ((1, 1, 4, 4), (4, 4), (0, 0), (1, 1)),         # one window
+    ((2, 3, 6, 6), (2, 2), (1, 1), (3, 3)),         # stride > kernel: some inputs in no window
+]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+@pytest.mark.parametrize("ci", range(len(POOL_CASES)))
+def test_maxpool_vs_oracle(am, dt, ci):
+    shape, kernel, pad, stride = POOL_CASES[ci]
+    rng = np.random.default_rng(40 + ci)
+    x = rng.integers(-4, 5, shape).astype(NP[dt])          # many ties: the first maximum must win
+    x += (rng.random(shape) < 0.3).astype(NP[dt]) * rng.random(shape).astype(NP[dt])
+    widx, wp = O.maxpool2d(x, kernel, pad, stride)
+    idx, pooled = am.maxpool2d(dev(x), kernel, pad, stride)
+    assert np.array_equal(pooled.cpu().numpy(), wp)
+    assert np.array_equal(idx.cpu().numpy(), widx)
+    go = (rng.random(wp.shape) * 2 - 1).astype(NP[dt])
+    want = O.maxpool2d_backward(shape, widx, go)
+    got = am.maxpool2d_backward(shape, idx, dev(go)).cpu().numpy()             # overlap-safe path (last writer wins)
+    assert np.array_equal(got, want)
+    if stride[0] >= kernel[0] and stride[1] >= kernel[1]:
+        got2 = am.maxpool2d_backward(shape, idx, dev(go), windows_overlap=False).cpu().numpy()
+        assert np.array_equal(got2, want)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 13, 5), (64, 800, 500), (33, 500, 10), (4, 3, 130)])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_linear_vs_oracle(am, dt, shape, with_bias):
+    batch, fin, fout = shape
+    rng = np.random.default_rng(batch * 7 + fout)
+    x = (rng.random((batch, fin)) * 2 - 1).astype(NP[dt]); w = (rng.random((fout, fin)) - 0.5).astype(NP[dt])
+    b = rng.random((1, fout)).astype(NP[dt]) if with_bias else None
+    go = (rng.random((batch, fout)) * 2 - 1).astype(NP[dt])
+    tol = 5e-6 if dt == "f32" else 1e-13
+    want = O.linear(x.astype(np.float64), w.astype(np.float64), None if b is None else b.astype(np.float64))
+    got = am.linear(dev(x), dev(w), dev(b) if with_bias else None).cpu().numpy()
+    assert rel(got, want) <= tol
+    wgi, wgw, wgb = O.linear_backward(x.astype(np.float64), w.astype(np.float64), go.astype(np.float64), with_bias)
+    gi, gw, gb = am.linear_backward(dev(x), dev(w), dev(go), with_bias)
+    assert rel(gi.cpu().numpy(), wgi) <= tol and rel(gw.cpu().numpy(), wgw) <= tol
+    if with_bias:
+        assert gb.shape == (1, fout) and rel(gb.cpu().numpy().reshape(-1), wgb) <= tol
+    else:
+        assert gb is None
+
+
+def test_softmax_ce_reference_vector(am):
+    c = KA.SOFTMAX_CE
+    pred = np.array(c["predicted"], dtype=np.float64)
+    lab = np.array(c["sparse_truth"], dtype=np.int64)
+    loss = am.sparse_softmax_cross_entropy(dev(pred), dev(lab))
+    assert abs(loss - c["loss"]) <= c["tol"]
+    g = am.sparse_softmax_cross_entropy_backward(loss, dev(pred), dev(lab)).cpu().numpy()
+    want = O.sparse_softmax_cross_entropy_backward(loss, pred, lab)
+    assert np.mean(np.abs(g - want) / np.maximum(np.abs(g), np.abs(want))) < c["grad_mre_tol"]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+@pytest.mark.parametrize("shape", [(256, 20), (4096, 10), (3, 1), (17, 1000)])
+def test_softmax_ce_vs_oracle(am, dt, shape):
+    # test_nnp_loss.nim:62-99: batch 256, 20 classes, predictions in [-1, 1)
+    rng = np.random.default_rng(1234)
+    pred = rng.uniform(-1, 1, shape).astype(NP[dt])
+    if shape[1] > 3:
+        pred[0, 1] = 30.0; pred[1, 2] = -30.0           # a dominant and a negligible logit
+    lab = rng.integers(0, shape[1], shape[0]).astype(np.int64)
+    want = float(O.sparse_softmax_cross_entropy(pred.astype(np.float64), lab))
+    got = am.sparse_softmax_cross_entropy(dev(pred), dev(lab))
+    tol = 2e-5 if dt == "f32" else 1e-12               # the reference's own `~=` for float32
+    assert abs(got - want) <= tol * max(1.0, abs(want))
+    wg = O.sparse_softmax_cross_entropy_backward(0.5, pred.astype(np.float64), lab)
+    g = am.sparse_softmax_cross_entropy_backward(0.5, dev(pred), dev(lab)).cpu().numpy()
+    assert rel(g, wg) <= (2e-6 if dt == "f32" else 1e-13)
+    # strided (transposed-view) input goes through rowStride / colStride
+    got_t = am.sparse_softmax_cross_entropy(dev(np.ascontiguousarray(pred.T)).t(), dev(lab))
+    assert abs(got_t - got) <= 1e-6 * max(1.0, abs(got))
+
+
+def test_empty_batches(am):
+    z = torch.empty((0, 10), device="cuda")
+    assert am.sparse_softmax_cross_entropy(z, torch.empty((0,), dtype=torch.int64, device="cuda")) == 0.0
+    assert am.relu(torch.empty((0,), device="cuda")).numel() == 0
+    y = am.linear(torch.empty((0, 5), device="cuda"), torch.ones((3, 5), device="cuda"))
+    assert tuple(y.shape) == (0, 3)
+
+
+def test_errors(am):
+    with pytest.raises(ValueError):
+        am.relu(torch.zeros(4))                                    # CPU tensor: no fallback
+    with pytest.raises(IndexError):
+        am.linear(torch.zeros((2, 3), device="cuda"), torch.zeros((4, 5), device="cuda"))
+    with pytest.raises(TypeError):
+        am.relu(torch.zeros(4, dtype=torch.int32, device="cuda"))
+
+
+def test_lenet_step_resident(am):
+    """ex02_mnist.nim's network, forward + backward on the device, against the oracle pipeline:
+    conv(1->20,5x5) relu pool2 conv(20->50,5x5) relu pool2 flatten linear(800->500) relu linear(500->10) sparse-CE."""
+    from oracle import laser_oracle as orc
+    rng = np.random.default_rng(7)
+    B = 16
+    x = rng.random((B, 1, 28, 28)).astype(np.float32)
+    w1 = (rng.standard_normal((20, 1, 5, 5)) * np.sqrt(2 / 25)).astype(np.float32); b1 = np.zeros((20, 1, 1), np.float32)
+    w2 = (rng.standard_normal((50, 20, 5, 5)) * np.sqrt(2 / 500)).astype(np.float32); b2 = (rng.random((50, 1, 1)) * 0.1).astype(np.float32)
+    w3 = (rng.standard_normal((500, 800)) * np.sqrt(2 / 800)).astype(np.float32); b3 = (rng.random((1, 500)) * 0.1).astype(np.float32)
+    w4 = (rng.standard_normal((10, 500)) * np.sqrt(2 / 500)).astype(np.float32); b4 = np.zeros((1, 10), np.float32)
+    lab = rng.integers(0, 10, B).astype(np.int64)
+
+    # ---- oracle pipeline (CPU)
+    c1 = orc.conv2d(x, w1, b1); r1 = O.relu(c1); i1, p1 = O.maxpool2d(r1, (2, 2), (0, 0), (2, 2))
+    c2 = orc.conv2d(p1, w2, b2); r2 = O.relu(c2); i2, p2 = O.maxpool2d(r2, (2, 2), (0, 0), (2, 2))
+    f = p2.reshape(B, 800)
+    h = O.linear(f, w3, b3); rh = O.relu(h); logits = O.linear(rh, w4, b4)
+    loss = float(O.sparse_softmax_cross_entropy(logits, lab))
+    gl = O.sparse_softmax_cross_entropy_backward(np.float32(1), logits, lab)
+    grh, gw4, gb4 = O.linear_backward(rh, w4, gl)
+    gh = O.relu_backward(grh, h)
+    gf, gw3, gb3 = O.linear_backward(f, w3, gh)
+    gr2 = O.maxpool2d_backward(r2.shape, i2, gf.reshape(p2.shape)); gc2 = O.relu_backward(gr2, c2)
+    gp1, gw2, gb2 = orc.conv2d_backward(p1, w2, gc2)
+    gr1 = O.maxpool2d_backward(r1.shape, i1, gp1); gc1 = O.relu_backward(gr1, c1)
+    gx, gw1, gb1 = orc.conv2d_backward(x, w1, gc1)
+
+    # ---- device pipeline (everything stays on the GPU until the final comparisons)
+    X, W1, B1, W2, B2, W3, B3, W4, B4, L = (dev(v) for v in (x, w1, b1, w2, b2, w3, b3, w4, b4, lab))
+    C1 = am.conv2d(X, W1, B1); R1 = am.relu(C1); I1, P1 = am.maxpool2d(R1, (2, 2), (0, 0), (2, 2))
+    C2 = am.conv2d(P1, W2, B2); R2 = am.relu(C2); I2, P2 = am.maxpool2d(R2, (2, 2), (0, 0), (2, 2))
+    F = P2.reshape(B, 800)
+    H = am.linear(F, W3, B3); RH = am.relu(H); LG = am.linear(RH, W4, B4)
+    dloss = am.sparse_softmax_cross_entropy(LG, L)
+    GL = am.sparse_softmax_cross_entropy_backward(1.0, LG, L)
+    GRH, GW4, GB4 = am.linear_backward(RH, W4, GL)
+    GH = am.relu_backward(GRH, H)
+    GF, GW3, GB3 = am.linear_backward(F, W3, GH)
+    GR2 = am.maxpool2d_backward(R2.shape, I2, GF.reshape(P2.shape), windows_overlap=False); GC2 = am.relu_backward(GR2, C2)
+    GP1, GW2, GB2 = am.conv2d_backward(P1, W2, B2, (0, 0), (1, 1), (1, 1), GC2)
+    GR1 = am.maxpool2d_backward(R1.shape, I1, GP1, windows_overlap=False); GC1 = am.relu_backward(GR1, C1)
+    GX, GW1, GB1 = am.conv2d_backward(X, W1, B1, (0, 0), (1, 1), (1, 1), GC1)
+
+    assert abs(dloss - loss) <= 2e-5 * max(1.0, abs(loss))
+    assert rel(LG.cpu().numpy(), logits) <= 2e-5
+    for name, got, want in (("gw4", GW4, gw4), ("gb4", GB4, gb4), ("gw3", GW3, gw3), ("gb3", GB3, gb3), ("gw2", GW2, gw2),
+                            ("gb2", GB2, gb2), ("gw1", GW1, gw1), ("gb1", GB1, gb1), ("gx", GX, gx)):
+        # argmax / relu masks can flip on near-ties between the GPU and CPU pipelines; at batch 16 with these inputs they
+        # do not, and the gradients agree to the backward tolerance
+        assert rel(got.cpu().numpy().reshape(np.asarray(want).shape), want) <= 2e-4, name

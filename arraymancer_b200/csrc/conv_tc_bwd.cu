@@ -215,7 +215,6 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
     const int ncols = cpc_here * KK;                            // D columns in use
     const float* col_p = reinterpret_cast<const float*>(smem_raw + (col_base - ptx::smem_u32(smem_raw)));
     float* img_p = reinterpret_cast<float*>(smem_raw + (img_base - ptx::smem_u32(smem_raw)));
-    const float* zero_p = img_p + img_floats;                   // one word that stays 0.0f
     for (uint32_t i = tid; i < img_floats + 4; i += 512) img_p[i] = 0.f;
     int ppos = prow;                                            // where this thread's pixel goes inside a col_s column
     if (a.padded) {
@@ -266,9 +265,19 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
           uint32_t r32[32];                                      // this warp's 32 columns in one go (reads past ncols are harmless)
           ptx::tmem_ld_32x32(td + (uint32_t)(cgrp * 32), r32);
           ptx::tmem_ld_wait();
+          if (ppos >= 0) {
+            const int nleft = ncols - cgrp * 32;                 // columns of this group that exist
+            if (a.padded) {                                      // constant column pitch: one address + immediate offsets
+              uint32_t* dst = reinterpret_cast<uint32_t*>(const_cast<float*>(col_p)) + cgrp * 32 * kPadColL + ppos;
 #pragma unroll
-          for (int e = 0; e < 32; e++)
-            if (cgrp * 32 + e < ncols && ppos >= 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col_base + (uint32_t)((cgrp * 32 + e) * a.colL + ppos) * 4u), "r"(r32[e]) : "memory");
+              for (int e = 0; e < 32; e++)
+                if (e < nleft) dst[e * kPadColL] = r32[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e++)
+                if (e < nleft) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col_base + (uint32_t)((cgrp * 32 + e) * a.colL + ppos) * 4u), "r"(r32[e]) : "memory");
+            }
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();

@@ -45,21 +45,51 @@ class RowShardedGemm:
     """C[M,N] = A[M,K] @ B[K,N] with A's rows dealt over the ranks and the full C gathered on every
     rank.  `A_local` holds this rank's rows ([chunks*mc, K], chunk-major); `B` is replicated."""
 
-    def __init__(self, M: int, N: int, K: int, dtype, device, chunks: int = 4, group=None, local_gemm=None):
+    def __init__(self, M: int, N: int, K: int, dtype, device, chunks: int = 4, group=None, local_gemm=None,
+                 fused: bool = False):
+        """fused=True (float32, CUDA, world > 1): C lives in symmetric memory and the GEMM epilogue stores every
+        tile to all GPUs' copies (am_gemm_packed_f32_bcast) — no NCCL collective, one launch per chunk."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.M, self.N, self.K, self.chunks = M, N, K, chunks
         self.mc = chunk_rows(M, self.world, chunks)
-        self.C = torch.empty((M, N), dtype=dtype, device=device)      # full result, row-major
         self.cuda = torch.device(device).type == "cuda"
+        self.sym = None
+        if fused and self.cuda and self.world > 1:
+            if dtype != torch.float32:
+                raise TypeError("RowShardedGemm(fused=True) is the float32 tcgen05 path")
+            self.sym = SymmetricResult((M, N), dtype, device, group)
+            self.C = self.sym.C
+            self._pA = self._pB = None
+        else:
+            self.C = torch.empty((M, N), dtype=dtype, device=device)  # full result, row-major
         if local_gemm is None:
             from .cuda_tensor import gemm_strided
             local_gemm = lambda A, B, C: gemm_strided(1, A, B, 0, C)  # noqa: E731
         self.local_gemm = local_gemm
         self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
 
+    def _call_fused(self, A_local: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        from .cuda_tensor import PackedF32, gemm_packed_bcast
+        g, r, mc = self.world, self.rank, self.mc
+        if self._pB is None:
+            self._pB = PackedF32(B, "b")
+            self._pA = PackedF32(A_local[:mc], "a")
+        else:
+            self._pB.repack(B)
+        for j in range(self.chunks):
+            lo = (j * g + r) * mc
+            mine = self.C[lo:lo + mc]
+            if j > 0 or self._pA is not None:
+                self._pA.repack(A_local[j * mc:(j + 1) * mc])
+            gemm_packed_bcast(1.0, self._pA, self._pB, mine, self.sym.peer_ptrs(mine), self.sym.rank)
+        self.sym.barrier()
+        return self.C
+
     def __call__(self, A_local: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        if self.sym is not None:
+            return self._call_fused(A_local, B)
         g, r, mc = self.world, self.rank, self.mc
         works = []
         for j in range(self.chunks):

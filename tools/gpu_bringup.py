@@ -250,7 +250,59 @@ def exp_conv_speed():
     return res
 
 
-EXPERIMENTS = ["peaks", "peaks_small_n", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed", "f64_speed",
+def exp_nn_speed():
+    """HBM-bound LeNet companions (batch 4096): achieved GB/s (algorithmic bytes) and a resident LeNet fwd+bwd step."""
+    import torch
+    import arraymancer_b200 as am
+    res = {}
+    B = 4096
+    x = torch.rand((B, 20, 24, 24), device="cuda") - 0.5
+    g = torch.rand_like(x)
+    nb = x.numel() * 4
+    med, _ = _time_gpu(lambda: am.relu(x), reps=5); res["relu_fwd_cv1"] = {"ms": med, "GBps": 2 * nb / med / 1e6}
+    med, _ = _time_gpu(lambda: am.relu_backward(g, x), reps=5); res["relu_bwd_cv1"] = {"ms": med, "GBps": 3 * nb / med / 1e6}
+    idx, p = am.maxpool2d(x, (2, 2), (0, 0), (2, 2))
+    med, _ = _time_gpu(lambda: am.maxpool2d(x, (2, 2), (0, 0), (2, 2)), reps=5)
+    res["maxpool_fwd_cv1"] = {"ms": med, "GBps": (nb + p.numel() * 4 + idx.numel() * 8) / med / 1e6}
+    gp = torch.rand_like(p)
+    med, _ = _time_gpu(lambda: am.maxpool2d_backward(x.shape, idx, gp, windows_overlap=False), reps=5)
+    res["maxpool_bwd_cv1"] = {"ms": med, "GBps": (nb + p.numel() * 4 + idx.numel() * 8) / med / 1e6}
+    f = torch.rand((B, 800), device="cuda"); w = torch.rand((500, 800), device="cuda") - 0.5; b = torch.rand((1, 500), device="cuda")
+    med, _ = _time_gpu(lambda: am.linear(f, w, b), reps=5); res["linear_fwd_800_500"] = {"ms": med, "tflops": 2 * B * 800 * 500 / med / 1e9}
+    go = torch.rand((B, 500), device="cuda")
+    med, _ = _time_gpu(lambda: am.linear_backward(f, w, go), reps=5); res["linear_bwd_800_500"] = {"ms": med, "tflops": 4 * B * 800 * 500 / med / 1e9}
+    lg = torch.rand((B, 10), device="cuda"); lab = torch.randint(0, 10, (B,), device="cuda")
+    med, _ = _time_gpu(lambda: am.sparse_softmax_cross_entropy_dev(lg, lab), reps=5); res["ssce_fwd"] = {"ms": med}
+    med, _ = _time_gpu(lambda: am.sparse_softmax_cross_entropy_backward(1.0, lg, lab), reps=5); res["ssce_bwd"] = {"ms": med}
+
+    # resident LeNet step (ex02_mnist.nim network), forward + backward, batch 4096
+    X = torch.rand((B, 1, 28, 28), device="cuda")
+    W1 = torch.randn((20, 1, 5, 5), device="cuda") * 0.28; B1 = torch.zeros((20, 1, 1), device="cuda")
+    W2 = torch.randn((50, 20, 5, 5), device="cuda") * 0.063; B2 = torch.zeros((50, 1, 1), device="cuda")
+    W3 = torch.randn((500, 800), device="cuda") * 0.05; B3 = torch.zeros((1, 500), device="cuda")
+    W4 = torch.randn((10, 500), device="cuda") * 0.063; B4 = torch.zeros((1, 10), device="cuda")
+
+    def step():
+        C1 = am.conv2d(X, W1, B1); R1 = am.relu(C1); I1, P1 = am.maxpool2d(R1, (2, 2), (0, 0), (2, 2))
+        C2 = am.conv2d(P1, W2, B2); R2 = am.relu(C2); I2, P2 = am.maxpool2d(R2, (2, 2), (0, 0), (2, 2))
+        F = P2.reshape(B, 800)
+        H = am.linear(F, W3, B3); RH = am.relu(H); LG = am.linear(RH, W4, B4)
+        loss = am.sparse_softmax_cross_entropy_dev(LG, lab)
+        GL = am.sparse_softmax_cross_entropy_backward(1.0, LG, lab)
+        GRH, GW4, GB4 = am.linear_backward(RH, W4, GL)
+        GH = am.relu_backward(GRH, H)
+        GF, GW3, GB3 = am.linear_backward(F, W3, GH)
+        GC2 = am.relu_backward(am.maxpool2d_backward(R2.shape, I2, GF.reshape(P2.shape), windows_overlap=False), C2)
+        GP1, GW2, GB2 = am.conv2d_backward(P1, W2, B2, (0, 0), (1, 1), (1, 1), GC2)
+        GC1 = am.relu_backward(am.maxpool2d_backward(R1.shape, I1, GP1, windows_overlap=False), C1)
+        am.conv2d_backward(X, W1, B1, (0, 0), (1, 1), (1, 1), GC1, need_input_grad=False)
+        return loss
+    med, best = _time_gpu(step, reps=5)
+    res["lenet_step_b4096"] = {"ms": med, "ms_best": best, "images_per_s": B / med * 1e3}
+    return res
+
+
+EXPERIMENTS = ["peaks", "nn_speed", "peaks_small_n", "simt_parity", "conv_parity", "tc1_f2", "tc2_f1", "tc2_f2", "tc2_f4", "tc2_f8", "simt_speed", "f64_speed",
                "tc1_speed_f2", "tc2_speed_f1", "tc2_speed_f2", "tc2_speed_f4", "tc2_speed_f8", "conv_speed"]
 
 

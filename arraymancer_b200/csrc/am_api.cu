@@ -95,10 +95,11 @@ static int gemm_f32_dispatch(cudaStream_t st, int64_t M, int64_t N, int64_t K, f
   if (path == AM_F32_TC) return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   if (path == AM_F32_TC_1CTA) return gemm_f32_tc(st, 1, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   if (path == AM_F32_AUTO && gemm_f32_tc_available()) {
-    // tensor tiles are 256x512 (pair) / 128x256: worth it once the output fills a wave of them and K
-    // amortises the split/pack pre-pass (an extra pass over A and B).
+    // worth it once K amortises the split/pack pre-pass (an extra pass over A and B) and there are a few output
+    // tiles: measured crossover vs the SIMT kernel is around 3 GFLOP (LeNet's 4096x800x500 linear layer: 0.084 vs
+    // 0.137 ms forward, 0.29 vs 0.385 ms backward; profiles/r01_bringup.md)
     const double flops = 2.0 * (double)M * (double)N * (double)K;
-    if (M >= 512 && N >= 512 && K >= 256 && flops >= 2.0e10)
+    if (M >= 256 && N >= 256 && K >= 256 && flops >= 3.0e9)
       return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   }
   return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);

@@ -183,20 +183,23 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         const bool ok = gq < npix;
         const int il = ok ? gq / HWo : 0, pix = ok ? gq - il * HWo : 0;
         const float* src = a.gout + ((n0 + il) * a.CO) * (int64_t)HWo + pix;
+        // all of the pixel's channels in flight at once (one L2 round trip per tile instead of one per 16 channels),
+        // issued before waiting for the operand stage so the latency overlaps the previous tile's MMAs
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; j++) v[j] = (ok && j < a.CO) ? __ldg(src + (int64_t)j * HWo) : 0.f;
         { const long long t0_ = clock64(); ptx::mbar_wait(a_empty(s), ((it >> 1) & 1u) ^ 1u); w_ae += clock64() - t0_; }
         ptx::tc_fence_after();
         const uint32_t ta = t_lane + (uint32_t)s * 2u * (uint32_t)a.Kpad;
-        for (int c0 = 0; c0 < a.Kpad; c0 += 16) {
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++) v[j] = (ok && c0 + j < a.CO) ? __ldg(src + (int64_t)(c0 + j) * HWo) : 0.f;
-          uint32_t hi[16], lo[16];
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          if (c0 < a.Kpad) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            ptx::split_tf32(v[j], hi[j], lo[j]);
+            for (int j = 0; j < 16; j++) ptx::split_tf32(v[c0 + j], hi[j], lo[j]);
+            ptx::tmem_st_32x16(ta + (uint32_t)c0, hi);
+            ptx::tmem_st_32x16(ta + (uint32_t)a.Kpad + (uint32_t)c0, lo);
           }
-          ptx::tmem_st_32x16(ta + (uint32_t)c0, hi);
-          ptx::tmem_st_32x16(ta + (uint32_t)a.Kpad + (uint32_t)c0, lo);
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();

@@ -137,6 +137,35 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
     idx[o] = arg;
   }
 }
+// 2x2 / stride 2 / no padding, float32, W % 4 == 0 (LeNet's pools): a thread takes two neighbouring windows from two
+// 128-bit loads and writes its two results with one 64-bit and one 128-bit store; same scan order and tie rule
+__global__ void maxpool_2x2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t* __restrict__ idx,
+                                       int64_t npairs, int H, int W, int Ho, int Wo) {
+  const int wp = Wo >> 1;                                   // output pairs per row
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < npairs; t += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(t % wp);
+    const int64_t t1 = t / wp;
+    const int h = (int)(t1 % Ho);
+    const int64_t nc = t1 / Ho;
+    const int64_t base = nc * (int64_t)H * W + (int64_t)(2 * h) * W + 4 * pw;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(x + base));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(x + base + W));
+    float b0 = -INFINITY, b1 = -INFINITY;
+    int64_t a0 = INT64_MIN, a1 = INT64_MIN;
+    if (r0.x > b0) { b0 = r0.x; a0 = base; }
+    if (r0.y > b0) { b0 = r0.y; a0 = base + 1; }
+    if (r1.x > b0) { b0 = r1.x; a0 = base + W; }
+    if (r1.y > b0) { b0 = r1.y; a0 = base + W + 1; }
+    if (r0.z > b1) { b1 = r0.z; a1 = base + 2; }
+    if (r0.w > b1) { b1 = r0.w; a1 = base + 3; }
+    if (r1.z > b1) { b1 = r1.z; a1 = base + W + 2; }
+    if (r1.w > b1) { b1 = r1.w; a1 = base + W + 3; }
+    const int64_t o = (nc * Ho + h) * (int64_t)Wo + 2 * pw;
+    *reinterpret_cast<float2*>(y + o) = make_float2(b0, b1);
+    *reinterpret_cast<longlong2*>(idx + o) = make_longlong2(a0, a1);
+  }
+}
+
 // gradInput[max_indices[i]] = gradOutput[i] (assignment, nnp_maxpooling.nim:82-83).  With overlapping windows the
 // serial reference keeps the LAST i: pass 1 records the largest i per input slot, pass 2 lets only that i write.
 __global__ void maxpool_owner_kernel(const int64_t* __restrict__ idx, long long* __restrict__ owner, int64_t n_out, int64_t n_in) {
@@ -165,6 +194,15 @@ int maxpool2d_forward(cudaStream_t st, int64_t N, int64_t C, int64_t H, int64_t 
   const int64_t total = N * C * Ho * Wo;
   if (total == 0) return AM_OK;
   if (!x || !y || !idx) { set_last_error("maxpool2d_forward: null pointer"); return AM_ERR_INVALID; }
+  if constexpr (std::is_same<T, float>::value) {
+    if (kH == 2 && kW == 2 && sH == 2 && sW == 2 && padH == 0 && padW == 0 && W % 4 == 0 && H % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15) == 0) {
+      maxpool_2x2_f32_kernel<<<grid_for(total / 2, 256), 256, 0, st>>>(x, y, idx, total / 2, (int)H, (int)W, (int)Ho, (int)Wo);
+      g_launch_count++;
+      AM_CUDA_TRY(cudaGetLastError());
+      return AM_OK;
+    }
+  }
   maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(x, y, idx, total, (int)C, (int)H, (int)W, (int)Ho, (int)Wo,
                                                              (int)kH, (int)kW, (int)padH, (int)padW, (int)sH, (int)sW);
   g_launch_count++;

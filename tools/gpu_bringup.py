@@ -271,6 +271,12 @@ def exp_nn_speed():
     med, _ = _time_gpu(lambda: am.linear(f, w, b), reps=5); res["linear_fwd_800_500"] = {"ms": med, "tflops": 2 * B * 800 * 500 / med / 1e9}
     go = torch.rand((B, 500), device="cuda")
     med, _ = _time_gpu(lambda: am.linear_backward(f, w, go), reps=5); res["linear_bwd_800_500"] = {"ms": med, "tflops": 4 * B * 800 * 500 / med / 1e9}
+    am.set_f32_path(am.F32_TC)
+    try:
+        med, _ = _time_gpu(lambda: am.linear(f, w, b), reps=5); res["linear_fwd_800_500_tc"] = {"ms": med, "tflops": 2 * B * 800 * 500 / med / 1e9}
+        med, _ = _time_gpu(lambda: am.linear_backward(f, w, go), reps=5); res["linear_bwd_800_500_tc"] = {"ms": med, "tflops": 4 * B * 800 * 500 / med / 1e9}
+    finally:
+        am.set_f32_path(am.F32_AUTO)
     lg = torch.rand((B, 10), device="cuda"); lab = torch.randint(0, 10, (B,), device="cuda")
     med, _ = _time_gpu(lambda: am.sparse_softmax_cross_entropy_dev(lg, lab), reps=5); res["ssce_fwd"] = {"ms": med}
     med, _ = _time_gpu(lambda: am.sparse_softmax_cross_entropy_backward(1.0, lg, lab), reps=5); res["ssce_bwd"] = {"ms": med}

@@ -363,6 +363,30 @@ def test_prepacked_operands(am, oracle):
     pa.free(); pb.free()
 
 
+def test_fused_allgather_epilogue_on_one_gpu(am, oracle):
+    """am_gemm_packed_f32_bcast (row-sharded GEMM + all-gather in one kernel) with every "peer" copy of C on this GPU:
+    exercises the local store + trickled peer copies of the epilogue, incl. edge tiles, several tiles per cluster,
+    a short K (few chains per tile: the whole tile is forwarded at once) and a column-major C."""
+    for (M, N, K) in [(700, 600, 1000), (2050, 1030, 96), (513, 4100, 2048)]:
+        a, b = rand((M, K), "f32", 61), rand((K, N), "f32", 62)
+        pa, pb = am.PackedF32(dev(a), "a"), am.PackedF32(dev(b), "b")
+        R = oracle.matmul(a, b)
+        for order in ("C", "F"):
+            for npeers, me in ((1, 0), (3, 1), (8, 7)):
+                # one buffer holding all copies, guard rows in between: nothing may be written outside the views
+                full = torch.full((npeers, M + 2, N), -7.0, device="cuda")
+                if order == "F":
+                    full = full.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+                views = [full[g, 1:M + 1] for g in range(npeers)]
+                am.gemm_packed_bcast(1.0, pa, pb, views[me], [v.data_ptr() for v in views], me)
+                torch.cuda.synchronize()
+                for g in range(npeers):
+                    assert rel_fro(views[g].cpu().numpy(), R) <= F32_TOL, (M, N, K, order, npeers, g)
+                    assert torch.equal(views[g], views[me])
+                assert bool((full[:, 0] == -7.0).all()) and bool((full[:, M + 1] == -7.0).all())
+        pa.free(); pb.free()
+
+
 def test_cpp_host_mirror_known_answers():
     """The C++ host-side mirror (arraymancer_b200/host/arraymancer_b200.hpp) — CudaTensor, cuda(), `*`, gemm, conv2d,
     conv2d_backward over the C ABI — replays the reference's CUDA test vectors (tests/cpp/test_host_mirror.cpp)."""

@@ -105,6 +105,136 @@ static int gemm_f32_dispatch(cudaStream_t st, int64_t M, int64_t N, int64_t K, f
   return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
 }
 
+
+// Large row-major float32 products from HOST buffers: K-pipelined schedule.  With row chunks alone (host_gemm below)
+// the first product cannot start before all of B is on the device (a third of the whole PCIe time); splitting K makes
+// the work that is computable grow LINEARLY with the bytes that have arrived:
+//   phase 1  the first half of K in 4 slices: slice c of A (M x kc, 2-D copy) and of B (kc x N, contiguous rows) is
+//            uploaded, split/packed and multiplied into the full C (beta = 0, then 1) while slice c+1 uploads;
+//   phase 2  by the time phase 1 has computed, the second half of K has arrived: it is processed by ROW chunks
+//            (C_i += A_i[:, K1:] * B[K1:, :]), each finished chunk of C going back to the host while the next computes.
+// 32768^3: 365 ms (row chunks only) -> ~300 ms; the device-resident step is 273 ms.
+static int host_gemm_f32_kpipelined(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA, const float* B,
+                                    int64_t rsB, float* C, int64_t rsC) {
+  const int NS = 4;                                          // K slices of phase 1
+  int dev = 0;
+  AM_CUDA_TRY(cudaGetDevice(&dev));
+  {
+    cudaMemPool_t pool;                                       // keep freed blocks cached in the stream-ordered pool between calls
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  const int64_t K1 = (K / 2) / (32 * NS) * (32 * NS), kc = K1 / NS, K2 = K - K1;
+  const int64_t rows = ((M / 8 + 255) / 256) * 256;           // row chunk of phase 2
+  const int nrc = (int)((M + rows - 1) / rows);
+  const int64_t last_rows = M - (int64_t)(nrc - 1) * rows;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> ev1((size_t)NS, nullptr), evA2((size_t)nrc, nullptr), evC((size_t)nrc, nullptr);
+  cudaEvent_t evB2 = nullptr, ev_alloc = nullptr;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *pk = nullptr;
+  void *hA1 = nullptr, *hB1 = nullptr, *hB2 = nullptr, *hA2 = nullptr, *hA2l = nullptr;
+  int status = AM_OK;
+  cudaError_t e = cudaSuccess;
+  const int64_t fA1 = packed_floats_f32(M, kc), fB1 = packed_floats_f32(N, kc), fB2 = packed_floats_f32(N, K2),
+                fA2 = packed_floats_f32(rows, K2);
+  static const bool dbg = getenv("AM_HOST_DEBUG") != nullptr;      // print the timeline of uploads / products
+  auto mk = [&](cudaEvent_t* ev) { return cudaEventCreateWithFlags(ev, dbg ? cudaEventDefault : cudaEventDisableTiming); };
+  cudaEvent_t ev_t0 = nullptr, ev_p1 = nullptr;
+  do {
+    if (dbg) { cudaEventCreate(&ev_t0); cudaEventCreate(&ev_p1); }
+    if ((e = cudaMallocAsync(&dA, (size_t)(M * K) * 4, s_in)) != cudaSuccess || (e = cudaMallocAsync(&dB, (size_t)(K * N) * 4, s_in)) != cudaSuccess ||
+        (e = cudaMallocAsync(&dC, (size_t)(M * N) * 4, s_in)) != cudaSuccess ||
+        (e = cudaMallocAsync(&pk, (size_t)(fA1 + fB1 + fB2 + fA2) * 4, s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocAsync"); break; }
+    float* pA1 = pk; float* pB1 = pA1 + fA1; float* pB2 = pB1 + fB1; float* pA2 = pB2 + fB2;
+    if ((e = mk(&ev_alloc)) != cudaSuccess || (e = mk(&evB2)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+    cudaEventRecord(ev_alloc, s_in);
+    if (dbg) cudaEventRecord(ev_t0, s_in);
+    cudaStreamWaitEvent(s_cmp, ev_alloc, 0);
+    cudaStreamWaitEvent(s_out, ev_alloc, 0);
+    // ---- uploads, in the order the products need them (one stream: the PCIe link is the shared resource)
+    for (int c = 0; c < NS && !status; c++) {
+      const int64_t k0 = c * kc;
+      if ((e = mk(&ev1[c])) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+      if ((e = cudaMemcpy2DAsync(dB + k0 * N, (size_t)N * 4, B + k0 * rsB, (size_t)rsB * 4, (size_t)N * 4, (size_t)kc, cudaMemcpyHostToDevice, s_in)) != cudaSuccess ||
+          (e = cudaMemcpy2DAsync(dA + k0, (size_t)K * 4, A + k0, (size_t)rsA * 4, (size_t)kc * 4, (size_t)M, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D K slice"); break; }
+      cudaEventRecord(ev1[c], s_in);
+    }
+    if (status) break;
+    if ((e = cudaMemcpy2DAsync(dB + K1 * N, (size_t)N * 4, B + K1 * rsB, (size_t)rsB * 4, (size_t)N * 4, (size_t)K2, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D B tail"); break; }
+    cudaEventRecord(evB2, s_in);
+    for (int i = 0; i < nrc && !status; i++) {
+      const int64_t r0 = (int64_t)i * rows, nr = (i == nrc - 1) ? last_rows : rows;
+      if ((e = mk(&evA2[i])) != cudaSuccess || (e = mk(&evC[i])) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+      if ((e = cudaMemcpy2DAsync(dA + r0 * K + K1, (size_t)K * 4, A + r0 * rsA + K1, (size_t)rsA * 4, (size_t)K2 * 4, (size_t)nr, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A tail"); break; }
+      cudaEventRecord(evA2[i], s_in);
+    }
+    if (status) break;
+    // ---- phase 1: K slices over the whole C
+    for (int c = 0; c < NS && !status; c++) {
+      const int64_t k0 = c * kc;
+      cudaStreamWaitEvent(s_cmp, ev1[c], 0);
+      if (c == 0) {
+        if ((status = pack_f32_view(s_cmp, M, kc, dA + k0, K, 1, pA1, &hA1))) break;
+        if ((status = pack_f32_view(s_cmp, N, kc, dB + k0 * N, 1, N, pB1, &hB1))) break;
+      } else {
+        if ((status = repack_f32(s_cmp, hA1, dA + k0, K, 1))) break;
+        if ((status = repack_f32(s_cmp, hB1, dB + k0 * N, 1, N))) break;
+      }
+      status = gemm_packed_f32(s_cmp, alpha, hA1, hB1, c == 0 ? 0.f : 1.f, dC, N, 1);
+    }
+    if (status) break;
+    if (dbg) cudaEventRecord(ev_p1, s_cmp);
+    // ---- phase 2: the rest of K by row chunks, results streaming back
+    cudaStreamWaitEvent(s_cmp, evB2, 0);
+    if ((status = pack_f32_view(s_cmp, N, K2, dB + K1 * N, 1, N, pB2, &hB2))) break;
+    for (int i = 0; i < nrc && !status; i++) {
+      const int64_t r0 = (int64_t)i * rows, nr = (i == nrc - 1) ? last_rows : rows;
+      cudaStreamWaitEvent(s_cmp, evA2[i], 0);
+      void** hh = (nr == rows) ? &hA2 : &hA2l;
+      if (*hh == nullptr) status = pack_f32_view(s_cmp, nr, K2, dA + r0 * K + K1, K, 1, pA2, hh);
+      else status = repack_f32(s_cmp, *hh, dA + r0 * K + K1, K, 1);
+      if (status) break;
+      if ((status = gemm_packed_f32(s_cmp, alpha, *hh, hB2, 1.f, dC + r0 * N, N, 1))) break;
+      cudaEventRecord(evC[i], s_cmp);
+      cudaStreamWaitEvent(s_out, evC[i], 0);
+      if ((e = cudaMemcpy2DAsync(C + r0 * rsC, (size_t)rsC * 4, dC + r0 * N, (size_t)N * 4, (size_t)N * 4, (size_t)nr, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) { status = cuda_fail(e, "D2H C chunk"); break; }
+    }
+  } while (0);
+  if ((e = cudaStreamSynchronize(s_in)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if ((e = cudaStreamSynchronize(s_cmp)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
+  if (dbg && !status && ev_t0) {
+    auto ms = [&](cudaEvent_t ev) { float t = -1.f; if (ev) cudaEventElapsedTime(&t, ev_t0, ev); return t; };
+    fprintf(stderr, "[host_gemm kpipe] uploads done: slices");
+    for (auto ev : ev1) fprintf(stderr, " %.1f", ms(ev));
+    fprintf(stderr, " | B tail %.1f | A tail chunks", ms(evB2));
+    for (auto ev : evA2) fprintf(stderr, " %.1f", ms(ev));
+    fprintf(stderr, " || phase 1 computed %.1f | row chunks computed", ms(ev_p1));
+    for (auto ev : evC) fprintf(stderr, " %.1f", ms(ev));
+    fprintf(stderr, " ms\n");
+  }
+  if (ev_t0) cudaEventDestroy(ev_t0);
+  if (ev_p1) cudaEventDestroy(ev_p1);
+  for (void* h : {hA1, hB1, hB2, hA2, hA2l}) if (h) packed_free_f32(h);
+  if (dA) cudaFreeAsync(dA, s_in);
+  if (dB) cudaFreeAsync(dB, s_in);
+  if (dC) cudaFreeAsync(dC, s_in);
+  if (pk) cudaFreeAsync(pk, s_in);
+  cudaStreamSynchronize(s_in);
+  for (auto ev : ev1) if (ev) cudaEventDestroy(ev);
+  for (auto ev : evA2) if (ev) cudaEventDestroy(ev);
+  for (auto ev : evC) if (ev) cudaEventDestroy(ev);
+  if (evB2) cudaEventDestroy(evB2);
+  if (ev_alloc) cudaEventDestroy(ev_alloc);
+  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
+  return status;
+}
+
 // host-buffer GEMM: what `a.cuda * b.cuda` then `.cpu` does (init_cuda.nim:23-59), as one call.
 // Row-major-like A and C are processed in row chunks on three streams — H2D of chunk j+1, GEMM of chunk j and
 // D2H of chunk j-1 overlap — after B has been copied (and, for f32, split/packed) once.
@@ -396,7 +526,22 @@ DEF_NN(f64, double)
         },                                                                                                      \
         M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);                                           \
   }
-DEF_HOST(f32, float)
+int am_host_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA, int64_t csA,
+                             const float* B, int64_t rsB, int64_t csB, float beta, float* C, int64_t rsC, int64_t csC) {
+  // large row-major products on the tensor cores: K-pipelined uploads (see host_gemm_f32_kpipelined)
+  static const bool no_kpipe = getenv("AM_HOST_ROWCHUNKS") != nullptr;
+  const int path = g_f32_path.load();
+  if (!no_kpipe && (path == AM_F32_AUTO || path == AM_F32_TC) && A && B && C && beta == 0.f && csA == 1 && csB == 1 && csC == 1 &&
+      rsA >= K && rsB >= N && rsC >= N && M >= 4096 && N >= 4096 && K >= 4096 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) &&
+      gemm_f32_tc_available())
+    return host_gemm_f32_kpipelined(M, N, K, alpha, A, rsA, B, rsB, C, rsC);
+  return host_gemm<float>(
+      [](cudaStream_t st, int64_t m, int64_t n, int64_t k, float al, const float* a, int64_t ra, int64_t ca, const float* b,
+         int64_t rb, int64_t cb, float be, float* c, int64_t rc_, int64_t cc) {
+        return am_gemm_strided_f32((am_stream_t)st, m, n, k, al, a, ra, ca, b, rb, cb, be, c, rc_, cc);
+      },
+      M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+}
 DEF_HOST(f64, double)
 DEF_HOST(i32, int32_t)
 DEF_HOST(i64, int64_t)

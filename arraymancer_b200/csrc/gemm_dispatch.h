@@ -26,6 +26,9 @@ bool gemm_f32_tc_available();
 // pre-packed operands (two tf32 planes, K-major): pack once, multiply many
 int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, void** handle);
 int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride);
+int64_t packed_floats_f32(int64_t R, int64_t K);
+int pack_f32_view(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, float* planes,
+                  void** handle);
 int packed_free_f32(void* handle);
 int gemm_packed_f32_bcast(cudaStream_t st, float alpha, const void* hA, const void* hB, int npeers, float* const* peers,
                           int self, int64_t rsC, int64_t csC);

@@ -608,6 +608,19 @@ int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_st
   *handle = p;
   return AM_OK;
 }
+// packed operand over caller-provided device memory (stream-ordered allocations of the host-buffer GEMM): `planes`
+// holds packed_floats_f32(R, K) floats; the handle does not own them (packed_free_f32 only drops the descriptor)
+int64_t packed_floats_f32(int64_t R, int64_t K) { return 2 * pad_rows(R) * pad_k(K); }
+int pack_f32_view(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, float* planes,
+                  void** handle) {
+  if (!gemm_f32_tc_available()) { set_last_error("tcgen05 path needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  if (R <= 0 || K <= 0 || !X || !handle || !planes) { set_last_error("pack_f32_view: bad argument"); return AM_ERR_INVALID; }
+  PackedF32* p = new PackedF32{planes, planes + pad_rows(R) * pad_k(K), R, K, pad_rows(R), pad_k(K), false};
+  int rc = pack_into(st, X, R, K, r_stride, k_stride, p);
+  if (rc) { delete p; return rc; }
+  *handle = p;
+  return AM_OK;
+}
 int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride) {
   PackedF32* p = (PackedF32*)handle;
   if (!p || !X) { set_last_error("am_repack_f32: bad argument"); return AM_ERR_INVALID; }

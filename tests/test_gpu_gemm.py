@@ -345,6 +345,28 @@ def test_host_buffer_entry(am, oracle):
             assert rel_fro(c, want) <= (F32_TOL if dt == "f32" else F64_TOL)
 
 
+def test_host_entry_k_pipelined(am, oracle):
+    """Large row-major float32 products through am_host_gemm_strided_f32 take the K-pipelined schedule (K slices
+    accumulated with beta = 1, then row chunks): uneven last row chunk, K not a multiple of the slice size, padded
+    host rows; compared with the device-resident product and with oracle rows."""
+    from arraymancer_b200 import _capi
+    M, N, K = 4352, 4096, 4160
+    a = rand((M, K + 8), "f32", 71)[:, :K]           # row pitch > K
+    b = rand((K, N), "f32", 72)
+    c = np.full((M, N + 16), np.float32(-5))          # row pitch > N: the gaps must survive
+    cv = c[:, :N]
+    lib = _capi.lib()
+    _capi.check(lib.am_host_gemm_strided_f32(M, N, K, 1.0, a.ctypes.data, a.strides[0] // 4, 1, b.ctypes.data, N, 1, 0.0,
+                                             cv.ctypes.data, c.strides[0] // 4, 1))
+    assert np.all(c[:, N:] == -5)
+    D = torch.empty((M, N), device="cuda")
+    am.gemm_strided(1, dev(np.ascontiguousarray(a)), dev(b), 0, D)
+    assert rel_fro(cv, D.cpu().numpy()) <= 2e-6
+    rows = [0, 1, 543, 544, 2175, M - 1]
+    want = oracle.matmul(np.ascontiguousarray(a[rows]), b)
+    assert rel_fro(cv[rows], want) <= F32_TOL
+
+
 def test_prepacked_operands(am, oracle):
     a, b = rand((700, 1000), "f32", 41), rand((1000, 600), "f32", 42)
     pa, pb = am.PackedF32(dev(a), "a"), am.PackedF32(dev(b), "b")

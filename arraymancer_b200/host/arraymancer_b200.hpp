@@ -194,4 +194,126 @@ void conv2d_backward(const CudaTensor<T>& input, const CudaTensor<T>& kernel, co
                                    has_bias ? grad_bias.get_offset_ptr() : nullptr));
 }
 
+
+// ---- the operators around the contractions, float32 / float64, C-contiguous tensors
+namespace detail {
+template <class T> struct NnAbi;
+#define AMB200_NN(T, SUF)                                                                                              \
+  template <> struct NnAbi<T> {                                                                                        \
+    static int relu(am_stream_t s, int64_t n, const T* x, T* y) { return am_relu_forward_##SUF(s, n, x, y); }          \
+    static int relu_bwd(am_stream_t s, int64_t n, const T* g, const T* c, T* o) { return am_relu_backward_##SUF(s, n, g, c, o); } \
+    static int pool(am_stream_t s, int64_t N, int64_t C, int64_t H, int64_t W, int64_t kH, int64_t kW, int64_t pH, int64_t pW, \
+                    int64_t sH, int64_t sW, const T* x, T* y, int64_t* idx) {                                          \
+      return am_maxpool2d_forward_##SUF(s, N, C, H, W, kH, kW, pH, pW, sH, sW, x, y, idx);                             \
+    }                                                                                                                  \
+    static int pool_bwd(am_stream_t s, int64_t nin, int64_t nout, const int64_t* idx, const T* go, T* gi, int ov) {    \
+      return am_maxpool2d_backward_##SUF(s, nin, nout, idx, go, gi, ov);                                               \
+    }                                                                                                                  \
+    static int linear(am_stream_t s, int64_t b, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y) { \
+      return am_linear_forward_##SUF(s, b, in, out, x, w, bias, y);                                                    \
+    }                                                                                                                  \
+    static int linear_bwd(am_stream_t s, int64_t b, int64_t in, int64_t out, const T* x, const T* w, const T* go, T* gi, \
+                          T* gw, T* gb) {                                                                              \
+      return am_linear_backward_##SUF(s, b, in, out, x, w, go, gi, gw, gb);                                            \
+    }                                                                                                                  \
+    static int ssce(am_stream_t s, int64_t b, int64_t f, const T* x, int64_t rs, int64_t cs, const int64_t* lab, T* loss) { \
+      return am_sparse_softmax_cross_entropy_##SUF(s, b, f, x, rs, cs, lab, loss);                                     \
+    }                                                                                                                  \
+    static int ssce_bwd(am_stream_t s, int64_t b, int64_t f, T g, const T* x, int64_t rs, int64_t cs, const int64_t* lab, \
+                        T* out) {                                                                                      \
+      return am_sparse_softmax_cross_entropy_backward_##SUF(s, b, f, g, x, rs, cs, lab, out);                          \
+    }                                                                                                                  \
+  };
+AMB200_NN(float, f32)
+AMB200_NN(double, f64)
+#undef AMB200_NN
+}  // namespace detail
+
+// relu / relu_backward — nnp_activation.nim:35-36, 65-70
+template <class T>
+CudaTensor<T> relu(const CudaTensor<T>& t, cudaStream_t st = nullptr) {
+  CudaTensor<T> out = CudaTensor<T>::make(t.shape, false);
+  amCheck(detail::NnAbi<T>::relu((am_stream_t)st, t.size(), t.get_offset_ptr(), out.get_offset_ptr()));
+  return out;
+}
+template <class T>
+CudaTensor<T> relu_backward(const CudaTensor<T>& gradient, const CudaTensor<T>& cached, cudaStream_t st = nullptr) {
+  if (gradient.shape != cached.shape) throw std::out_of_range("relu_backward: shapes differ");
+  CudaTensor<T> out = CudaTensor<T>::make(gradient.shape, false);
+  amCheck(detail::NnAbi<T>::relu_bwd((am_stream_t)st, gradient.size(), gradient.get_offset_ptr(), cached.get_offset_ptr(),
+                                     out.get_offset_ptr()));
+  return out;
+}
+
+// maxpool2d(input, kernel, padding, stride) -> (max_indices, maxpooled) — nnp_maxpooling.nim:19-66
+template <class T>
+struct MaxPoolResult { CudaTensor<int64_t> max_indices; CudaTensor<T> maxpooled; };
+template <class T>
+MaxPoolResult<T> maxpool2d(const CudaTensor<T>& input, SizeHW kernel, SizeHW padding = {0, 0}, SizeHW stride = {1, 1},
+                           cudaStream_t st = nullptr) {
+  if (input.rank() != 4) throw std::invalid_argument("maxpool2d: input must be rank-4 NCHW");
+  const int64_t N = input.shape[0], C = input.shape[1], H = input.shape[2], W = input.shape[3];
+  const int64_t oh = (H + 2 * padding[0] - kernel[0]) / stride[0] + 1, ow = (W + 2 * padding[1] - kernel[1]) / stride[1] + 1;
+  if (oh < 1 || ow < 1) throw std::invalid_argument("maxpool2d: kernel larger than the padded input");
+  MaxPoolResult<T> r;
+  r.max_indices = CudaTensor<int64_t>::make({N * C * oh * ow}, false);
+  r.maxpooled = CudaTensor<T>::make({N, C, oh, ow}, false);
+  amCheck(detail::NnAbi<T>::pool((am_stream_t)st, N, C, H, W, kernel[0], kernel[1], padding[0], padding[1], stride[0], stride[1],
+                                 input.get_offset_ptr(), r.maxpooled.get_offset_ptr(), r.max_indices.get_offset_ptr()));
+  return r;
+}
+// maxpool2d_backward(cached_input_shape, cached_max_indices, gradOutput) — nnp_maxpooling.nim:68-83
+template <class T>
+CudaTensor<T> maxpool2d_backward(const std::vector<int64_t>& input_shape, const CudaTensor<int64_t>& max_indices,
+                                 const CudaTensor<T>& grad_output, bool windows_overlap = true, cudaStream_t st = nullptr) {
+  if (max_indices.size() != grad_output.size()) throw std::out_of_range("maxpool2d_backward: sizes differ");
+  CudaTensor<T> gi = CudaTensor<T>::make(input_shape, false);
+  amCheck(detail::NnAbi<T>::pool_bwd((am_stream_t)st, gi.size(), grad_output.size(), max_indices.get_offset_ptr(),
+                                     grad_output.get_offset_ptr(), gi.get_offset_ptr(), windows_overlap ? 1 : 0));
+  return gi;
+}
+
+// linear(input [batch,in], weight [out,in], bias [1,out] or rank-0) -> [batch,out] — nnp_linear.nim:20-37
+template <class T>
+CudaTensor<T> linear(const CudaTensor<T>& input, const CudaTensor<T>& weight, const CudaTensor<T>& bias, cudaStream_t st = nullptr) {
+  if (input.rank() != 2 || weight.rank() != 2 || input.shape[1] != weight.shape[1]) throw std::out_of_range("linear: shapes do not match");
+  CudaTensor<T> out = CudaTensor<T>::make({input.shape[0], weight.shape[0]}, false);
+  amCheck(detail::NnAbi<T>::linear((am_stream_t)st, input.shape[0], input.shape[1], weight.shape[0], input.get_offset_ptr(),
+                                   weight.get_offset_ptr(), bias.rank() > 0 ? bias.get_offset_ptr() : nullptr, out.get_offset_ptr()));
+  return out;
+}
+// linear_backward(input, weight, gradOutput, gradInput, gradWeight, gradBias) — nnp_linear.nim:39-66
+template <class T>
+void linear_backward(const CudaTensor<T>& input, const CudaTensor<T>& weight, const CudaTensor<T>& grad_output,
+                     CudaTensor<T>& grad_input, CudaTensor<T>& grad_weight, CudaTensor<T>* grad_bias, cudaStream_t st = nullptr) {
+  grad_input = CudaTensor<T>::make(input.shape, false);
+  grad_weight = CudaTensor<T>::make(weight.shape, false);
+  if (grad_bias) *grad_bias = CudaTensor<T>::make({1, weight.shape[0]}, false);
+  amCheck(detail::NnAbi<T>::linear_bwd((am_stream_t)st, input.shape[0], input.shape[1], weight.shape[0], input.get_offset_ptr(),
+                                       weight.get_offset_ptr(), grad_output.get_offset_ptr(), grad_input.get_offset_ptr(),
+                                       grad_weight.get_offset_ptr(), grad_bias ? grad_bias->get_offset_ptr() : nullptr));
+}
+
+// sparse_softmax_cross_entropy(input [batch,features], target [batch]) -> scalar — nnp_softmax_cross_entropy.nim:100-178
+template <class T>
+T sparse_softmax_cross_entropy(const CudaTensor<T>& input, const CudaTensor<int64_t>& target, cudaStream_t st = nullptr) {
+  if (input.rank() != 2 || target.size() != input.shape[0]) throw std::out_of_range("sparse_softmax_cross_entropy: shapes do not match");
+  CudaTensor<T> loss = CudaTensor<T>::make({1}, false);
+  amCheck(detail::NnAbi<T>::ssce((am_stream_t)st, input.shape[0], input.shape[1], input.get_offset_ptr(), input.strides[0],
+                                 input.strides[1], target.get_offset_ptr(), loss.get_offset_ptr()));
+  T h;
+  cudaCheck(cudaMemcpyAsync(&h, loss.get_offset_ptr(), sizeof(T), cudaMemcpyDeviceToHost, st));
+  cudaCheck(cudaStreamSynchronize(st));
+  return h;
+}
+// sparse_softmax_cross_entropy_backward(gradient, cached, target) — nnp_softmax_cross_entropy.nim:219-252
+template <class T>
+CudaTensor<T> sparse_softmax_cross_entropy_backward(T gradient, const CudaTensor<T>& cached, const CudaTensor<int64_t>& target,
+                                                    cudaStream_t st = nullptr) {
+  CudaTensor<T> out = CudaTensor<T>::make(cached.shape, false);
+  amCheck(detail::NnAbi<T>::ssce_bwd((am_stream_t)st, cached.shape[0], cached.shape[1], gradient, cached.get_offset_ptr(),
+                                     cached.strides[0], cached.strides[1], target.get_offset_ptr(), out.get_offset_ptr()));
+  return out;
+}
+
 }  // namespace arraymancer_b200

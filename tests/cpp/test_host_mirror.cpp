@@ -84,6 +84,49 @@ static void conv_known_answers() {
   EXPECT((gbh == std::vector<T>{9, 9}));
 }
 
+template <class T>
+static std::vector<T> raw(const CudaTensor<T>& t) {
+  std::vector<T> h((size_t)t.size());
+  cudaCheck(cudaMemcpy(h.data(), t.get_offset_ptr(), h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+template <class T>
+static void nn_known_answers() {
+  // tests/nn_primitives/test_nnp_maxpool.nim:21-32
+  auto a = nchw<T>({1, 1, 2, 4, 5, 6, 7, 8, 3, 2, 1, 0, 1, 2, 3, 4}, {1, 1, 4, 4});
+  auto mp = maxpool2d<T>(a, {2, 2}, {0, 0}, {2, 2});
+  EXPECT((raw(mp.maxpooled) == std::vector<T>{6, 8, 3, 4}));
+  EXPECT((raw(mp.max_indices) == std::vector<int64_t>{5, 7, 8, 15}));
+  auto g = maxpool2d_backward<T>(a.shape, mp.max_indices, mp.maxpooled);
+  EXPECT((raw(g) == std::vector<T>{0, 0, 0, 0, 0, 6, 0, 8, 3, 0, 0, 0, 0, 0, 0, 4}));
+  // relu / relu_backward — nnp_activation.nim:35-36, 65-70
+  auto x = nchw<T>({-1, 0, 2, -3}, {4});
+  EXPECT((raw(relu(x)) == std::vector<T>{0, 0, 2, 0}));
+  auto gr = nchw<T>({5, 6, 7, 8}, {4});
+  EXPECT((raw(relu_backward(gr, x)) == std::vector<T>{0, 0, 7, 0}));
+  // linear — nnp_linear.nim:20-66: y = x W^T + b on exact small integers
+  auto xi = nchw<T>({1, 2, 3, 4, 5, 6}, {2, 3});
+  auto w = nchw<T>({1, 0, -1, 2, 1, 0}, {2, 3});
+  auto b = nchw<T>({10, 20}, {1, 2});
+  EXPECT((raw(linear(xi, w, b)) == std::vector<T>{8, 24, 8, 33}));
+  CudaTensor<T> gi, gw, gb;
+  auto go = nchw<T>({1, 1, 2, 0}, {2, 2});
+  linear_backward(xi, w, go, gi, gw, &gb);
+  EXPECT((raw(gi) == std::vector<T>{3, 1, -1, 2, 0, -2}));
+  EXPECT((raw(gw) == std::vector<T>{9, 12, 15, 1, 2, 3}));
+  EXPECT((raw(gb) == std::vector<T>{3, 1}));
+  // tests/nn_primitives/test_nnp_loss.nim:29-44: loss ~= 0.0709 (|a - b| <= 2e-5)
+  auto pred = nchw<T>({T(-3.44), T(1.16), T(-0.81), T(3.91)}, {1, 4});
+  auto lab = nchw<int64_t>({3}, {1});
+  const T loss = sparse_softmax_cross_entropy(pred, lab);
+  EXPECT(std::fabs((double)loss - 0.0709) <= 2e-5);
+  auto gl = raw(sparse_softmax_cross_entropy_backward(T(1), pred, lab));
+  double sum = 0;
+  for (auto v : gl) sum += (double)v;
+  EXPECT(std::fabs(sum) < 1e-6 && gl[3] < 0 && gl[0] > 0);      // softmax - onehot sums to zero
+}
+
 int main() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { std::printf("SKIP: no GPU\n"); return 77; }
@@ -95,6 +138,8 @@ int main() {
   conv_known_answers<double>();
   conv_known_answers<int32_t>();
   conv_known_answers<int64_t>();
+  nn_known_answers<float>();
+  nn_known_answers<double>();
   am_shutdown();
   std::printf("OK %d checks\n", checks);
   return 0;

@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     + [f"am_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_host_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_conv2d_forward_{s}" for s in SUFFIXES]
+    + [f"am_conv2d_forward_act_{s}" for s in SUFFIXES]
     + [f"am_conv2d_backward_{s}" for s in SUFFIXES]
     + [f"am_{op}_{s}" for s in ("f32", "f64") for op in NN_OPS]
 )
@@ -73,6 +74,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"am_gemm_strided_{s}").argtypes = [p, i64, i64, i64, ct, p, i64, i64, p, i64, i64, ct, p, i64, i64]
         getattr(L, f"am_host_gemm_strided_{s}").argtypes = [i64, i64, i64, ct, p, i64, i64, p, i64, i64, ct, p, i64, i64]
         getattr(L, f"am_conv2d_forward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p]
+        getattr(L, f"am_conv2d_forward_act_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, ci]
         getattr(L, f"am_conv2d_backward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, p]
     f = ctypes.c_float
     L.am_pack_f32_a.argtypes = [p, i64, i64, p, i64, i64, ctypes.POINTER(p)]
@@ -122,6 +124,7 @@ def set_f64_path(path: int) -> None:
 
 
 CONV_AUTO, CONV_GATHER, CONV_DIRECT, CONV_TC = 0, 1, 2, 3
+ACT_NONE, ACT_RELU = 0, 1
 
 
 def set_conv_path(path: int) -> None:

@@ -475,6 +475,14 @@ int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
     if (!d) { set_last_error("conv2d_forward: null descriptor"); return AM_ERR_INVALID; }                      \
     return conv2d_forward<T>((cudaStream_t)s, *d, in, k, b, out);                                               \
   }                                                                                                             \
+  int am_conv2d_forward_act_##SUF(am_stream_t s, const am_conv2d_desc* d, const T* in, const T* k, const T* b,  \
+                                  T* out, int activation) {                                                     \
+    if (!d) { set_last_error("conv2d_forward: null descriptor"); return AM_ERR_INVALID; }                      \
+    if (activation != AM_ACT_NONE && activation != AM_ACT_RELU) {                                               \
+      set_last_error("conv2d_forward_act: unknown activation %d", activation); return AM_ERR_INVALID;           \
+    }                                                                                                           \
+    return conv2d_forward<T>((cudaStream_t)s, *d, in, k, b, out, activation);                                   \
+  }                                                                                                             \
   int am_conv2d_backward_##SUF(am_stream_t s, const am_conv2d_desc* d, const T* in, const T* k, const T* go,    \
                                T* gi, T* gk, T* gb) {                                                           \
     if (!d) { set_last_error("conv2d_backward: null descriptor"); return AM_ERR_INVALID; }                     \

@@ -178,7 +178,11 @@ struct Im2colRowsLoader {
 // rows = channels, columns = (image, pixel): dst[(n*CH + ch)*PIX + p] = v (+ bias[ch])
 template <class T>
 struct NchwEpilogue {
-  T* dst; const T* bias; int64_t CH, PIX, NCOLS; bool vec_ok;
+  T* dst; const T* bias; int64_t CH, PIX, NCOLS; bool vec_ok; bool relu;
+  __device__ __forceinline__ T fin(T v, T b) const {
+    const T s = add_nocontract<T>(v, b);
+    return (relu && s <= T(0)) ? T(0) : s;
+  }
   template <int V>
   __device__ __forceinline__ void store(int64_t ch, int64_t j0, const T (&v)[V], int) const {
     if (ch >= CH || j0 >= NCOLS) return;
@@ -188,7 +192,7 @@ struct NchwEpilogue {
       using Vec = typename std::conditional<sizeof(T) == 4, int4, longlong2>::type;
       union { Vec q; T e[V]; } o;
 #pragma unroll
-      for (int j = 0; j < V; j++) o.e[j] = add_nocontract<T>(v[j], b);
+      for (int j = 0; j < V; j++) o.e[j] = fin(v[j], b);
       *reinterpret_cast<Vec*>(dst + (n * CH + ch) * PIX + p) = o.q;
     } else {
 #pragma unroll
@@ -196,7 +200,7 @@ struct NchwEpilogue {
         const int64_t jj = j0 + j;
         if (jj < NCOLS) {
           const int64_t n = jj / PIX, p = jj - n * PIX;
-          dst[(n * CH + ch) * PIX + p] = add_nocontract<T>(v[j], b);
+          dst[(n * CH + ch) * PIX + p] = fin(v[j], b);
         }
       }
     }
@@ -296,14 +300,14 @@ static int launch_by_rows(cudaStream_t st, const LA& la, const LB& lb, const Epi
 
 // conv_direct.cu: float32 shared-memory-staged direct kernels (fast path); *done == false -> use the gather kernels
 int conv2d_forward_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
-                              const float* kernel, const float* bias, float* output, bool* done);
+                              const float* kernel, const float* bias, float* output, int act, bool* done);
 int conv2d_dgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
                             const float* kernel, float* grad_input, bool* done);
 int conv2d_wgrad_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
                             const float* grad_output, float** part_out, int* groups_out, bool* done);
 // conv_tc.cu: tcgen05 implicit-GEMM kernels (float32, Cout <= 64); *done == false -> next path
 int conv2d_forward_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
-                          const float* kernel, const float* bias, float* output, bool* done);
+                          const float* kernel, const float* bias, float* output, int act, bool* done);
 int conv2d_dgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* grad_output,
                         const float* kernel, float* grad_input, bool* done);
 // conv_tc_bwd.cu: data gradient as GEMM + col2im on the tensor cores (any stride / padding / dilation, Cout <= 64)
@@ -318,7 +322,7 @@ static bool auto_path() { return g_conv_path.load() == AM_CONV_AUTO; }
 
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
-                   T* output) {
+                   T* output, int act) {
   ConvGeom g;
   if (!make_geom(d, &g)) { set_last_error("conv2d_forward: invalid geometry"); return AM_ERR_INVALID; }
   if (g.Nimg == 0) return AM_OK;
@@ -327,12 +331,12 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
     // AUTO: the tcgen05 implicit GEMM pays once the GEMM is wide and deep enough (measured: LeNet cv2 yes, cv1 no)
     if (tc_enabled() || (auto_path() && d.Cout >= 32 && g.Kc >= 128)) {
       bool done = false;
-      int rcd = conv2d_forward_tc_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
+      int rcd = conv2d_forward_tc_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, act, &done);
       if (rcd || done) return rcd;
     }
     if (direct_enabled()) {
       bool done = false;
-      int rcd = conv2d_forward_direct_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, &done);
+      int rcd = conv2d_forward_direct_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, act, &done);
       if (rcd || done) return rcd;
     }
   }
@@ -344,7 +348,7 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   Im2colColsLoader<T> lb{input, tabF, g, NP};
   constexpr int V = 16 / (int)sizeof(T);
   NchwEpilogue<T> epi{output, bias, g.Cout, g.HoWo, NP,
-                      (g.HoWo % V == 0) && ((reinterpret_cast<uintptr_t>(output) & 15) == 0)};
+                      (g.HoWo % V == 0) && ((reinterpret_cast<uintptr_t>(output) & 15) == 0), act != 0};
   return launch_by_rows<T>(st, la, lb, epi, g.Cout, NP, g.Kc);
 }
 
@@ -379,7 +383,7 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
     WeightTLoader<T> la{kernel, tabW, g, KD};
     GradOutColsLoader<T> lb{grad_output, tabD, g, NQ, KD};
     NchwEpilogue<T> epi{grad_input, nullptr, g.C, g.HW, NQ,
-                        (g.HW % V == 0) && ((reinterpret_cast<uintptr_t>(grad_input) & 15) == 0)};
+                        (g.HW % V == 0) && ((reinterpret_cast<uintptr_t>(grad_input) & 15) == 0), false};
     rc = launch_by_rows<T>(st, la, lb, epi, g.C, NQ, KD);
     if (rc) return rc;
   }
@@ -437,7 +441,7 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
 }
 
 #define INST(T)                                                                                              \
-  template int conv2d_forward<T>(cudaStream_t, const am_conv2d_desc&, const T*, const T*, const T*, T*);     \
+  template int conv2d_forward<T>(cudaStream_t, const am_conv2d_desc&, const T*, const T*, const T*, T*, int); \
   template int conv2d_backward<T>(cudaStream_t, const am_conv2d_desc&, const T*, const T*, const T*, T*, T*, T*);
 INST(float)
 INST(double)

@@ -36,6 +36,7 @@ struct DirectArgs {
   int CO_B, CG, CI_B;           // output channels per CTA (padded), channel groups, input channels per block
   int bands;                    // ceil(HO / TH)
   int BUF_FLOATS;               // floats per half of the double-buffered stage (multiple of 4)
+  int relu;                     // fused activation: y = max(0, conv + bias) (nnp_activation.nim:35-36 semantics)
 };
 
 template <int CT, int PX, int KW>
@@ -147,7 +148,9 @@ conv_direct_f32_kernel(const DirectArgs a) {
     }
   }
 
-  // ---- epilogue: + bias, NCHW stores
+  // ---- epilogue: + bias (and the fused ReLU), NCHW stores
+  const bool relu = a.relu != 0;
+  auto act = [relu](float v) { return (relu && v <= 0.f) ? 0.f : v; };
   if (active) {
     const int wo0 = seg * PX;
     const int64_t chan_pix = (int64_t)a.HO * a.WO;
@@ -161,12 +164,12 @@ conv_direct_f32_kernel(const DirectArgs a) {
         if (wo0 + PX <= a.WO && ((reinterpret_cast<uintptr_t>(yc) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < PX; j += 4)
-            *reinterpret_cast<float4*>(yc + j) = make_float4(__fadd_rn(acc[c][j], b), __fadd_rn(acc[c][j + 1], b),
-                                                             __fadd_rn(acc[c][j + 2], b), __fadd_rn(acc[c][j + 3], b));
+            *reinterpret_cast<float4*>(yc + j) = make_float4(act(__fadd_rn(acc[c][j], b)), act(__fadd_rn(acc[c][j + 1], b)),
+                                                             act(__fadd_rn(acc[c][j + 2], b)), act(__fadd_rn(acc[c][j + 3], b)));
         } else {
 #pragma unroll
           for (int j = 0; j < PX; j++)
-            if (wo0 + j < a.WO) yc[j] = __fadd_rn(acc[c][j], b);
+            if (wo0 + j < a.WO) yc[j] = act(__fadd_rn(acc[c][j], b));
         }
       }
     }
@@ -289,10 +292,11 @@ static int launch_direct(cudaStream_t st, DirectArgs& a, int KW, bool* done) {
 
 // forward: y = conv(x, w) + bias.  *done = false -> caller must use the gather kernels.
 int conv2d_forward_direct_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
-                              const float* kernel, const float* bias, float* output, bool* done) {
+                              const float* kernel, const float* bias, float* output, int act, bool* done) {
   *done = false;
   if (d.strideH != 1 || d.strideW != 1 || d.dilH != 1 || d.dilW != 1) return AM_OK;
   DirectArgs a{};
+  a.relu = act;
   a.x = input; a.w = kernel; a.bias = bias; a.y = output; a.N = d.N;
   a.C = (int)d.C; a.H = (int)d.H; a.W = (int)d.W; a.CO = (int)d.Cout; a.kH = (int)d.kH;
   a.padH = (int)d.padH; a.padW = (int)d.padW; a.HO = (int)Ho; a.WO = (int)Wo;

@@ -46,6 +46,7 @@ struct ConvTcArgs {
   int groups;           // gather groups (of 128 threads)
   uint32_t raw_bytes;   // bytes of one raw-image buffer (max images a tile touches * CHW * 4, rounded up)
   long long* dbg;       // optional: per-role wait-cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
+  int relu;             // fused activation: y = max(0, conv + bias)
 };
 
 constexpr int kCtABytes = 128 * 128;      // one plane of the im2col tile: 128 pixels x 32 floats
@@ -351,7 +352,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
             const float bb[4] = {b0, b1, b2, b3};
 #pragma unroll
             for (int e = 0; e < 4; e++)
-              if (c4 * 4 + e < a.CO) yp[(c4 * 4 + e) * HW] = __fadd_rn(acc[c4 * 4 + e], bb[e]);
+              if (c4 * 4 + e < a.CO) {
+                const float v = __fadd_rn(acc[c4 * 4 + e], bb[e]);
+                yp[(c4 * 4 + e) * HW] = (a.relu && v <= 0.f) ? 0.f : v;
+              }
           }
         }
       }
@@ -376,6 +380,7 @@ struct ConvTcView {           // one convolution in "forward form": y = conv(x, 
   int64_t N;
   int C, H, W, CO, kH, kW, padH, padW, sH, sW, dH, dW, HO, WO;
   int64_t w_off, w_sco, w_sci, w_skh, w_skw;
+  int relu;
 };
 
 static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
@@ -434,7 +439,7 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
     if (r != CUDA_SUCCESS) { set_last_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AM_ERR_CUDA; }
   }
   ConvTcArgs a{};
-  a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N;
+  a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N; a.relu = v.relu;
   a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes;
   static int groups_env = 0;
   if (groups_env == 0) { const char* e = getenv("AM_CONVTC_GROUPS"); groups_env = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4; }
@@ -478,8 +483,9 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
 }
 
 int conv2d_forward_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
-                          const float* kernel, const float* bias, float* output, bool* done) {
+                          const float* kernel, const float* bias, float* output, int act, bool* done) {
   ConvTcView v{};
+  v.relu = act;
   v.x = input; v.w = kernel; v.bias = bias; v.y = output; v.N = d.N;
   v.C = (int)d.C; v.H = (int)d.H; v.W = (int)d.W; v.CO = (int)d.Cout; v.kH = (int)d.kH; v.kW = (int)d.kW;
   v.padH = (int)d.padH; v.padW = (int)d.padW; v.sH = (int)d.strideH; v.sW = (int)d.strideW; v.dH = (int)d.dilH; v.dW = (int)d.dilW;

@@ -43,7 +43,7 @@ int gemm_f64_dmma(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha
 // conv.cu
 template <class T>
 int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel, const T* bias,
-                   T* output);
+                   T* output, int act = 0);      // act: AM_ACT_NONE / AM_ACT_RELU fused into the epilogue
 template <class T>
 int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, const T* kernel,
                     const T* grad_output, T* grad_input, T* grad_kernel, T* grad_bias);

@@ -57,9 +57,12 @@ def _check_mem(*ts):
 
 
 def conv2d(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None = None,
-           padding=(0, 0), strides=(1, 1), dilation=(1, 1)) -> torch.Tensor:
+           padding=(0, 0), strides=(1, 1), dilation=(1, 1), activation: str | None = None) -> torch.Tensor:
     """Cross-correlation of NCHW `input` with `kernel` [Cout,Cin,kH,kW] plus `bias` [Cout,1,1]
-    (or None for the reference's rank-0 "no bias" tensor)."""
+    (or None for the reference's rank-0 "no bias" tensor).  activation="relu" fuses the reference's separate
+    `relu` pass (nnp_activation.nim:35-36) into the epilogue: max(0, conv + bias)."""
+    if activation not in (None, "relu"):
+        raise ValueError("conv2d: activation must be None or 'relu'")
     d = _desc(input, kernel, padding, strides, dilation)
     if bias is not None and bias.numel() == 0:
         bias = None
@@ -73,9 +76,14 @@ def conv2d(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None 
         raise ValueError("conv2d: kernel larger than the padded input")
     out = torch.empty(shape, dtype=input.dtype, device=input.device)
     with torch.cuda.device(input.device):
-        _capi.check(getattr(_capi.lib(), f"am_conv2d_forward_{suf}")(
-            _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(),
-            bias.data_ptr() if bias is not None else None, out.data_ptr()))
+        if activation is None:
+            _capi.check(getattr(_capi.lib(), f"am_conv2d_forward_{suf}")(
+                _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(),
+                bias.data_ptr() if bias is not None else None, out.data_ptr()))
+        else:
+            _capi.check(getattr(_capi.lib(), f"am_conv2d_forward_act_{suf}")(
+                _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(),
+                bias.data_ptr() if bias is not None else None, out.data_ptr(), _capi.ACT_RELU))
     return out
 
 

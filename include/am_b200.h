@@ -156,9 +156,17 @@ AM_API int am_conv2d_out_dims(const am_conv2d_desc* d, int64_t* Ho, int64_t* Wo)
 enum { AM_CONV_AUTO = 0, AM_CONV_GATHER = 1, AM_CONV_DIRECT = 2, AM_CONV_TC = 3 };
 AM_API int am_set_conv_path(int path);
 
+/* Epilogue fusion on the conv boundary: the reference adds the bias in a second pass
+ * (fallback/conv.nim:105-106, nnp_conv2d_cudnn.nim:72) and applies relu in a third (nnp_activation.nim:35-36);
+ * am_conv2d_forward_* fuses the bias, am_conv2d_forward_act_* also the activation: y = max(0, conv + bias) with
+ * the reference's relu semantics (value <= 0 -> 0, NaN stays NaN).  relu_backward on the stored output is
+ * equivalent to relu_backward on the pre-activation (output <= 0 exactly where pre-activation <= 0). */
+enum { AM_ACT_NONE = 0, AM_ACT_RELU = 1 };
 #define AM_DECL_CONV(SUF, T)                                                                     \
   AM_API int am_conv2d_forward_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input, \
                                      const T* kernel, const T* bias, T* output);                 \
+  AM_API int am_conv2d_forward_act_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input, \
+                                         const T* kernel, const T* bias, T* output, int activation); \
   /* grad_input / grad_kernel / grad_bias may each be NULL to skip that gradient */             \
   AM_API int am_conv2d_backward_##SUF(am_stream_t stream, const am_conv2d_desc* d,               \
                                       const T* input, const T* kernel, const T* grad_output,     \

@@ -18,11 +18,13 @@ def _header_symbols():
     # macro-declared families
     for suf in ("f32", "f64", "i32", "i64"):
         names.add(f"am_conv2d_forward_{suf}")
+        names.add(f"am_conv2d_forward_act_{suf}")
         names.add(f"am_conv2d_backward_{suf}")
     for suf in ("f32", "f64"):                                   # AM_DECL_NN(SUF, T)
         for op in _capi.NN_OPS:
             names.add(f"am_{op}_{suf}")
     names.discard("am_conv2d_forward_")
+    names.discard("am_conv2d_forward_act_")
     names.discard("am_conv2d_backward_")
     return {n for n in names if not n.endswith("_")}
 

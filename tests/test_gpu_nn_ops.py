@@ -139,6 +139,29 @@ def test_softmax_ce_vs_oracle(am, dt, shape):
     assert abs(got_t - got) <= 1e-6 * max(1.0, abs(got))
 
 
+@pytest.mark.parametrize("path", ["auto", "tc", "direct", "gather"])
+@pytest.mark.parametrize("dt", ["f32", "f64", "i32", "i64"])
+def test_conv_fused_relu_epilogue(am, path, dt):
+    """am_conv2d_forward_act_* == relu(am_conv2d_forward_*) bit for bit, in every kernel family."""
+    from arraymancer_b200 import _capi
+    npdt = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}[dt]
+    _capi.set_conv_path({"auto": _capi.CONV_AUTO, "tc": _capi.CONV_TC, "direct": _capi.CONV_DIRECT, "gather": _capi.CONV_GATHER}[path])
+    try:
+        for xs, ks, pad, st in [((3, 20, 12, 12), (50, 20, 5, 5), (0, 0), (1, 1)), ((2, 1, 28, 28), (20, 1, 5, 5), (0, 0), (1, 1)),
+                                ((2, 3, 9, 8), (5, 3, 3, 3), (1, 1), (2, 1))]:
+            rng = np.random.default_rng(5)
+            if dt.startswith("f"):
+                x = (rng.random(xs) - 0.5).astype(npdt); k = (rng.random(ks) - 0.5).astype(npdt); b = (rng.random((ks[0], 1, 1)) - 0.5).astype(npdt)
+            else:
+                x = rng.integers(-9, 9, xs).astype(npdt); k = rng.integers(-9, 9, ks).astype(npdt); b = rng.integers(-9, 9, (ks[0], 1, 1)).astype(npdt)
+            plain = am.conv2d(dev(x), dev(k), dev(b), pad, st)
+            fused = am.conv2d(dev(x), dev(k), dev(b), pad, st, activation="relu")
+            assert torch.equal(fused, torch.clamp_min(plain, 0))
+            assert float((fused == 0).float().mean()) > 0.05            # the test data does exercise the clamp
+    finally:
+        _capi.set_conv_path(_capi.CONV_AUTO)
+
+
 def test_empty_batches(am):
     z = torch.empty((0, 10), device="cuda")
     assert am.sparse_softmax_cross_entropy(z, torch.empty((0,), dtype=torch.int64, device="cuda")) == 0.0

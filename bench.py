@@ -94,6 +94,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use the whole host
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     import numpy as np
     from oracle import laser_oracle as orc
     orc.build()

@@ -219,7 +219,7 @@ int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64
   long long* owner = nullptr;
   if (windows_overlap) {
     void* ws = nullptr;
-    int rc = workspace(kWsConv, (size_t)n_in * sizeof(long long), &ws);
+    int rc = workspace(kWsNn, (size_t)n_in * sizeof(long long), &ws);
     if (rc) return rc;
     owner = (long long*)ws;
     AM_CUDA_TRY(cudaMemsetAsync(owner, 0x80, (size_t)n_in * sizeof(long long), st));      // very negative
@@ -367,7 +367,7 @@ int ssce_forward(cudaStream_t st, int64_t batch, int64_t features, const T* x, i
   if (batch == 0) { AM_CUDA_TRY(cudaMemsetAsync(loss_dev, 0, sizeof(T), st)); return AM_OK; }        // returns 0 (:128-130)
   if (!x || !labels) { set_last_error("sparse_softmax_cross_entropy: null pointer"); return AM_ERR_INVALID; }
   void* ws = nullptr;
-  int rc = workspace(kWsConv, (size_t)batch * sizeof(T), &ws);
+  int rc = workspace(kWsNn, (size_t)batch * sizeof(T), &ws);
   if (rc) return rc;
   ssce_rows_kernel<T><<<grid_for(batch, 128), 128, 0, st>>>(x, rs, cs, labels, batch, features, (T*)ws);
   mean_kernel<T><<<1, 256, 0, st>>>((const T*)ws, batch, loss_dev);

@@ -5,6 +5,10 @@
  * cross this boundary; am_last_error() returns the message of the last failure on the
  * calling thread.  All device entry points are asynchronous on the given stream and never
  * free or retain user pointers.  All paths are relative to /root/reference/src/arraymancer/.
+ * Concurrency: like the reference's single cudaStream0 / cublasHandle0 (backend/cuda_global_state.nim:21-39) the
+ * library keeps ONE set of scratch buffers per device (packed operand panels, conv partials, ...), ordered by the
+ * stream of the call that uses them: calls of the same family (GEMM, conv, NN ops) on one device must be issued on
+ * one stream (or be ordered by events); different devices and different families are independent.
  *
  * The reference-side bindings (Nim {.importc, cdecl, dynlib.}) are shown in INTEGRATION.md.
  */

@@ -335,6 +335,15 @@ def main():
             traffic = json.load(open(tp)).get("gemm_tf32x3_kernel", {}).get(f"n{n}_g{world}")
         except Exception:
             traffic = None
+    # the library's own tcgen05 kind::tf32 micro-benchmark (am_microbench 5, profiles/) gives a second denominator
+    own_peak = None
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", "r01_bringup_final.jsonl")):
+            d = json.loads(ln)
+            if d.get("exp") == "peaks":
+                own_peak = float(d["result"]["umma_tf32_1cta"]) / 3.0
+    except Exception:
+        own_peak = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -351,7 +360,9 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "kernel": "gemm_tf32x3_kernel<2>", "kernel_ms": kern_ms, "flops_per_launch": kern_flops,
-                     "peak_source": f"{src}: bf16_tflops_sustained / 2 (tf32 rate) / 3 (three tf32 MMAs per fp32 product)"},
+                     "peak_source": f"{src}: bf16_tflops_sustained / 2 (tf32 rate) / 3 (three tf32 MMAs per fp32 product)",
+                     "own_umma_tf32_peak_div3": own_peak,
+                     "frac_of_own_umma_peak": (achieved_tf / own_peak) if own_peak else None},
         "clocks": clocks, "gpu_launches": int(launches),
     }
     if e2e:

@@ -245,7 +245,8 @@ AM_API int64_t am_kernel_launch_count(void);
  *        4 = DMMA m8n8k4 f64 (mma.sync), 5 = tcgen05 kind::tf32 cta_group::1 128x256x8,
  *        6 = tcgen05 kind::tf32 cta_group::2 256x256x8, 7 = int64 accumulate of int32-range operands
  *        (one IMAD.WIDE per multiply-accumulate); 8..12 = tcgen05 kind::tf32 cta_group::1 at the small N the
- *        implicit-GEMM conv issues: 8 = 128x64x8 into one accumulator, 9 = alternating two accumulators,
+ *        implicit-GEMM conv issues (compile-time shapes, 16 unrolled MMAs per commit): 8 = 128x64x8 into one
+ *        accumulator, 9 = alternating two accumulators,
  *        10 = 128x64x8 with A read from tensor memory, 11 = same with two accumulators, 12 = 128x128x8.
  * Writes achieved 1e12 op/s (2 ops per multiply-add) to *tops. */
 AM_API int am_microbench(int which, double* tops);

@@ -24,12 +24,16 @@ NN_OPS = ("relu_forward", "relu_backward", "maxpool2d_forward", "maxpool2d_backw
 EXPORTED_SYMBOLS = (
     ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path", "am_set_conv_path",
      "am_cublas_gemm_f32", "am_cublas_gemm_f64", "am_pack_f32_a", "am_pack_f32_b", "am_repack_f32_a",
-     "am_repack_f32_b", "am_gemm_packed_f32", "am_gemm_packed_f32_bcast", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench"]
+     "am_repack_f32_b", "am_gemm_packed_f32", "am_gemm_packed_f32_bcast", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench",
+     "am_set_tuning", "am_get_tuning", "am_memcpy2d_async", "am_packed_floats_f32", "am_pack_f32_a_into", "am_pack_f32_b_into", "am_packed_wrap_f32"]
     + [f"am_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_host_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_conv2d_forward_{s}" for s in SUFFIXES]
     + [f"am_conv2d_forward_act_{s}" for s in SUFFIXES]
     + [f"am_conv2d_backward_{s}" for s in SUFFIXES]
+    + [f"am_conv2d_forward_strided_{s}" for s in SUFFIXES]
+    + [f"am_conv2d_backward_strided_{s}" for s in SUFFIXES]
+    + [f"am_gemm_strided_batched_{s}" for s in SUFFIXES]
     + [f"am_{op}_{s}" for s in ("f32", "f64") for op in NN_OPS]
 )
 
@@ -76,6 +80,10 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"am_conv2d_forward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p]
         getattr(L, f"am_conv2d_forward_act_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, ci]
         getattr(L, f"am_conv2d_backward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, p]
+        getattr(L, f"am_conv2d_forward_strided_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, i64, p, p, ci]
+        getattr(L, f"am_conv2d_backward_strided_{s}").argtypes = [p, ctypes.POINTER(ConvDesc)] + [p] * 12 + [i64]
+        getattr(L, f"am_gemm_strided_batched_{s}").argtypes = [p, i64, i64, i64, i64, ct, p, i64, i64, i64, p, i64, i64, i64,
+                                                               ct, p, i64, i64, i64]
     f = ctypes.c_float
     L.am_pack_f32_a.argtypes = [p, i64, i64, p, i64, i64, ctypes.POINTER(p)]
     L.am_pack_f32_b.argtypes = [p, i64, i64, p, i64, i64, ctypes.POINTER(p)]
@@ -84,6 +92,14 @@ def lib() -> ctypes.CDLL:
     L.am_gemm_packed_f32.argtypes = [p, f, p, p, f, p, i64, i64]
     L.am_gemm_packed_f32_bcast.argtypes = [p, f, p, p, ci, p, ci, i64, i64]
     L.am_packed_free_f32.argtypes = [p]
+    L.am_packed_floats_f32.argtypes = [i64, i64]
+    L.am_packed_floats_f32.restype = i64
+    L.am_pack_f32_a_into.argtypes = [p, i64, i64, p, i64, i64, p, ctypes.POINTER(p)]
+    L.am_pack_f32_b_into.argtypes = [p, i64, i64, p, i64, i64, p, ctypes.POINTER(p)]
+    L.am_packed_wrap_f32.argtypes = [i64, i64, p, ctypes.POINTER(p)]
+    L.am_memcpy2d_async.argtypes = [p, p, i64, p, i64, i64, i64, ci]
+    L.am_set_tuning.argtypes = [ctypes.c_char_p, ci]
+    L.am_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(ci)]
     for s in ("f32", "f64"):
         ct = CTYPE[s]
         getattr(L, f"am_cublas_gemm_{s}").argtypes = [p, ci, ci, i64, i64, i64, ct, p, i64, p, i64, ct, p, i64]
@@ -129,6 +145,17 @@ ACT_NONE, ACT_RELU = 0, 1
 
 def set_conv_path(path: int) -> None:
     check(lib().am_set_conv_path(path))
+
+
+def set_tuning(name: str, value: int) -> None:
+    """am_set_tuning: explicit process-wide tuning knob (the library reads no environment variables)."""
+    check(lib().am_set_tuning(name.encode(), int(value)))
+
+
+def get_tuning(name: str) -> int:
+    v = ctypes.c_int()
+    check(lib().am_get_tuning(name.encode(), ctypes.byref(v)))
+    return v.value
 
 
 def kernel_launch_count() -> int:

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -79,6 +80,81 @@ int sm_count() {
 static std::atomic<int> g_f32_path{AM_F32_AUTO};
 static std::atomic<int> g_f64_path{AM_F64_AUTO};
 
+// ------------------------------------------------------------------ explicit tuning knobs (no environment variables)
+static std::atomic<int> g_tune[kTuneCount] = {{2}, {8}, {1}, {0}, {0}, {0}, {0}, {0}, {1}};
+static const char* const kTuneNames[kTuneCount] = {"tc_flush_kb", "tc_group", "tc_sync", "pack_scalar", "host_rowchunks",
+                                                   "convtc_groups", "convtc_debug", "convtc_dgrad_gather", "simt_vec_load"};
+int tuning(int key) { return (key >= 0 && key < kTuneCount) ? g_tune[key].load(std::memory_order_relaxed) : 0; }
+static int tune_key(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < kTuneCount; i++) if (strcmp(name, kTuneNames[i]) == 0) return i;
+  return -1;
+}
+
+// ------------------------------------------------------------------ host-buffer entries: streams, events, memory pool
+// The host-buffer GEMMs keep, per calling thread and device, three non-blocking streams (H2D, compute, D2H) and a
+// growing list of timing-less events, and allocate their device buffers from ONE private stream-ordered pool per
+// device (not the device's default pool, which the host framework may share): freed blocks stay cached in it between
+// calls and are returned to the driver by am_shutdown().
+struct HostCtx {
+  int dev = -1;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t used = 0;
+  ~HostCtx() { release(); }
+  void release() {
+    for (auto e : events) cudaEventDestroy(e);
+    events.clear();
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_cmp) cudaStreamDestroy(s_cmp);
+    if (s_out) cudaStreamDestroy(s_out);
+    s_in = s_cmp = s_out = nullptr; dev = -1;
+  }
+  int init(int device) {
+    used = 0;
+    if (dev == device && s_in) return AM_OK;
+    release();
+    AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+    AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    dev = device;
+    return AM_OK;
+  }
+  cudaEvent_t event() {           // next cached event (nullptr on failure)
+    if (used == events.size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      events.push_back(e);
+    }
+    return events[used++];
+  }
+};
+static thread_local HostCtx t_host;
+
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[16] = {nullptr};
+static int host_pool(int dev, cudaMemPool_t* out) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev < 0 || dev >= 16) { set_last_error("host gemm: device index out of range"); return AM_ERR_INVALID; }
+  if (!g_pool[dev]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    AM_CUDA_TRY(cudaMemPoolCreate(&g_pool[dev], &props));
+    uint64_t thr = UINT64_MAX;                     // keep freed blocks cached between calls (trimmed by am_shutdown)
+    AM_CUDA_TRY(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  *out = g_pool[dev];
+  return AM_OK;
+}
+static void host_pools_release() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (int d = 0; d < 16; d++)
+    if (g_pool[d]) { cudaMemPoolDestroy(g_pool[d]); g_pool[d] = nullptr; }
+}
+
 template <class T>
 static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, const T* B, T* C) {
   if (M < 0 || N < 0 || K < 0) { set_last_error("gemm_strided: negative dimension"); return AM_ERR_INVALID; }
@@ -119,47 +195,39 @@ static int host_gemm_f32_kpipelined(int64_t M, int64_t N, int64_t K, float alpha
   const int NS = 4;                                          // K slices of phase 1
   int dev = 0;
   AM_CUDA_TRY(cudaGetDevice(&dev));
-  {
-    cudaMemPool_t pool;                                       // keep freed blocks cached in the stream-ordered pool between calls
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-  }
+  cudaMemPool_t pool;
+  int status = host_pool(dev, &pool);
+  if (status) return status;
+  HostCtx& hc = t_host;
+  if ((status = hc.init(dev))) return status;
+  cudaStream_t s_in = hc.s_in, s_cmp = hc.s_cmp, s_out = hc.s_out;
   const int64_t K1 = (K / 2) / (32 * NS) * (32 * NS), kc = K1 / NS, K2 = K - K1;
   const int64_t rows = ((M / 8 + 255) / 256) * 256;           // row chunk of phase 2
   const int nrc = (int)((M + rows - 1) / rows);
   const int64_t last_rows = M - (int64_t)(nrc - 1) * rows;
-  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  std::vector<cudaEvent_t> ev1((size_t)NS, nullptr), evA2((size_t)nrc, nullptr), evC((size_t)nrc, nullptr);
-  cudaEvent_t evB2 = nullptr, ev_alloc = nullptr;
   float *dA = nullptr, *dB = nullptr, *dC = nullptr, *pk = nullptr;
   void *hA1 = nullptr, *hB1 = nullptr, *hB2 = nullptr, *hA2 = nullptr, *hA2l = nullptr;
-  int status = AM_OK;
   cudaError_t e = cudaSuccess;
   const int64_t fA1 = packed_floats_f32(M, kc), fB1 = packed_floats_f32(N, kc), fB2 = packed_floats_f32(N, K2),
                 fA2 = packed_floats_f32(rows, K2);
-  static const bool dbg = getenv("AM_HOST_DEBUG") != nullptr;      // print the timeline of uploads / products
-  auto mk = [&](cudaEvent_t* ev) { return cudaEventCreateWithFlags(ev, dbg ? cudaEventDefault : cudaEventDisableTiming); };
-  cudaEvent_t ev_t0 = nullptr, ev_p1 = nullptr;
   do {
-    if (dbg) { cudaEventCreate(&ev_t0); cudaEventCreate(&ev_p1); }
-    if ((e = cudaMallocAsync(&dA, (size_t)(M * K) * 4, s_in)) != cudaSuccess || (e = cudaMallocAsync(&dB, (size_t)(K * N) * 4, s_in)) != cudaSuccess ||
-        (e = cudaMallocAsync(&dC, (size_t)(M * N) * 4, s_in)) != cudaSuccess ||
-        (e = cudaMallocAsync(&pk, (size_t)(fA1 + fB1 + fB2 + fA2) * 4, s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocAsync"); break; }
+    if ((e = cudaMallocFromPoolAsync((void**)&dA, (size_t)(M * K) * 4, pool, s_in)) != cudaSuccess ||
+        (e = cudaMallocFromPoolAsync((void**)&dB, (size_t)(K * N) * 4, pool, s_in)) != cudaSuccess ||
+        (e = cudaMallocFromPoolAsync((void**)&dC, (size_t)(M * N) * 4, pool, s_in)) != cudaSuccess ||
+        (e = cudaMallocFromPoolAsync((void**)&pk, (size_t)(fA1 + fB1 + fB2 + fA2) * 4, pool, s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocFromPoolAsync"); break; }
     float* pA1 = pk; float* pB1 = pA1 + fA1; float* pB2 = pB1 + fB1; float* pA2 = pB2 + fB2;
-    if ((e = mk(&ev_alloc)) != cudaSuccess || (e = mk(&evB2)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+    std::vector<cudaEvent_t> ev1((size_t)NS), evA2((size_t)nrc), evC((size_t)nrc);
+    cudaEvent_t ev_alloc = hc.event(), evB2 = hc.event();
+    for (auto& ev : ev1) ev = hc.event();
+    for (auto& ev : evA2) ev = hc.event();
+    for (auto& ev : evC) ev = hc.event();
+    if (!ev_alloc || !evB2 || !ev1.back() || !evA2.back() || !evC.back()) { status = cuda_fail(cudaErrorMemoryAllocation, "event"); break; }
     cudaEventRecord(ev_alloc, s_in);
-    if (dbg) cudaEventRecord(ev_t0, s_in);
     cudaStreamWaitEvent(s_cmp, ev_alloc, 0);
     cudaStreamWaitEvent(s_out, ev_alloc, 0);
     // ---- uploads, in the order the products need them (one stream: the PCIe link is the shared resource)
     for (int c = 0; c < NS && !status; c++) {
       const int64_t k0 = c * kc;
-      if ((e = mk(&ev1[c])) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
       if ((e = cudaMemcpy2DAsync(dB + k0 * N, (size_t)N * 4, B + k0 * rsB, (size_t)rsB * 4, (size_t)N * 4, (size_t)kc, cudaMemcpyHostToDevice, s_in)) != cudaSuccess ||
           (e = cudaMemcpy2DAsync(dA + k0, (size_t)K * 4, A + k0, (size_t)rsA * 4, (size_t)kc * 4, (size_t)M, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D K slice"); break; }
       cudaEventRecord(ev1[c], s_in);
@@ -169,7 +237,6 @@ static int host_gemm_f32_kpipelined(int64_t M, int64_t N, int64_t K, float alpha
     cudaEventRecord(evB2, s_in);
     for (int i = 0; i < nrc && !status; i++) {
       const int64_t r0 = (int64_t)i * rows, nr = (i == nrc - 1) ? last_rows : rows;
-      if ((e = mk(&evA2[i])) != cudaSuccess || (e = mk(&evC[i])) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
       if ((e = cudaMemcpy2DAsync(dA + r0 * K + K1, (size_t)K * 4, A + r0 * rsA + K1, (size_t)rsA * 4, (size_t)K2 * 4, (size_t)nr, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A tail"); break; }
       cudaEventRecord(evA2[i], s_in);
     }
@@ -188,7 +255,6 @@ static int host_gemm_f32_kpipelined(int64_t M, int64_t N, int64_t K, float alpha
       status = gemm_packed_f32(s_cmp, alpha, hA1, hB1, c == 0 ? 0.f : 1.f, dC, N, 1);
     }
     if (status) break;
-    if (dbg) cudaEventRecord(ev_p1, s_cmp);
     // ---- phase 2: the rest of K by row chunks, results streaming back
     cudaStreamWaitEvent(s_cmp, evB2, 0);
     if ((status = pack_f32_view(s_cmp, N, K2, dB + K1 * N, 1, N, pB2, &hB2))) break;
@@ -208,38 +274,19 @@ static int host_gemm_f32_kpipelined(int64_t M, int64_t N, int64_t K, float alpha
   if ((e = cudaStreamSynchronize(s_in)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
   if ((e = cudaStreamSynchronize(s_cmp)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
   if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess && !status) status = cuda_fail(e, "sync");
-  if (dbg && !status && ev_t0) {
-    auto ms = [&](cudaEvent_t ev) { float t = -1.f; if (ev) cudaEventElapsedTime(&t, ev_t0, ev); return t; };
-    fprintf(stderr, "[host_gemm kpipe] uploads done: slices");
-    for (auto ev : ev1) fprintf(stderr, " %.1f", ms(ev));
-    fprintf(stderr, " | B tail %.1f | A tail chunks", ms(evB2));
-    for (auto ev : evA2) fprintf(stderr, " %.1f", ms(ev));
-    fprintf(stderr, " || phase 1 computed %.1f | row chunks computed", ms(ev_p1));
-    for (auto ev : evC) fprintf(stderr, " %.1f", ms(ev));
-    fprintf(stderr, " ms\n");
-  }
-  if (ev_t0) cudaEventDestroy(ev_t0);
-  if (ev_p1) cudaEventDestroy(ev_p1);
   for (void* h : {hA1, hB1, hB2, hA2, hA2l}) if (h) packed_free_f32(h);
   if (dA) cudaFreeAsync(dA, s_in);
   if (dB) cudaFreeAsync(dB, s_in);
   if (dC) cudaFreeAsync(dC, s_in);
   if (pk) cudaFreeAsync(pk, s_in);
   cudaStreamSynchronize(s_in);
-  for (auto ev : ev1) if (ev) cudaEventDestroy(ev);
-  for (auto ev : evA2) if (ev) cudaEventDestroy(ev);
-  for (auto ev : evC) if (ev) cudaEventDestroy(ev);
-  if (evB2) cudaEventDestroy(evB2);
-  if (ev_alloc) cudaEventDestroy(ev_alloc);
-  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
   return status;
 }
 
 // host-buffer GEMM: what `a.cuda * b.cuda` then `.cpu` does (init_cuda.nim:23-59), as one call.
 // Row-major-like A and C are processed in row chunks on three streams — H2D of chunk j+1, GEMM of chunk j and
-// D2H of chunk j-1 overlap — after B has been copied (and, for f32, split/packed) once.
-bool g_reuse_packed_b = false;   // read by gemm_f32_tc: B was packed by the previous chunk of this host call
-
+// D2H of chunk j-1 overlap — after B has been copied once.  `device_gemm(stream, chunk_index, ...)` is the per-chunk
+// product; the float32 functor splits/packs B once (chunk 0) into an explicit handle and reuses it for the other chunks.
 template <class T, class F>
 static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
                      int64_t csA, const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) {
@@ -260,18 +307,16 @@ static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, 
 
   int dev = 0;
   AM_CUDA_TRY(cudaGetDevice(&dev));
-  static thread_local int pool_tuned_dev = -1;
-  if (pool_tuned_dev != dev) {       // keep freed blocks cached in the stream-ordered pool between calls
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    pool_tuned_dev = dev;
-  }
-  // row chunks: only when rows of A and of C are increasing, disjoint host ranges
-  const bool rowwise = rsA > 0 && csA > 0 && rsA >= csA * (K > 1 ? 1 : 0) && rsA >= (K - 1) * csA + 1 &&
-                       rsC > 0 && csC > 0 && rsC >= (N - 1) * csC + 1 && beta == T(0);
+  cudaMemPool_t pool;
+  int status = host_pool(dev, &pool);
+  if (status) return status;
+  HostCtx& hc = t_host;
+  if ((status = hc.init(dev))) return status;
+  cudaStream_t s_in = hc.s_in, s_cmp = hc.s_cmp, s_out = hc.s_out;
+  // row chunks: only when rows of A and of C are increasing, disjoint host ranges and C's rows are dense runs of N
+  // elements (csC == 1): each chunk of C then goes back with ONE 2-D copy that touches exactly the N valid elements of
+  // every row, so whatever the host holds between the rows (rsC > N) is left alone.
+  const bool rowwise = rsA > 0 && csA > 0 && rsA >= (K - 1) * csA + 1 && csC == 1 && rsC >= N && beta == T(0);
   int64_t chunk = M;
   if (rowwise && M >= 2048) {
     chunk = ((M / 8 + 255) / 256) * 256;
@@ -279,47 +324,41 @@ static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, 
   }
   const int nchunks = (int)((M + chunk - 1) / chunk);
 
-  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
-  AM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  std::vector<cudaEvent_t> ev_in((size_t)nchunks, nullptr), ev_cmp((size_t)nchunks, nullptr);
-  cudaEvent_t ev_alloc = nullptr;
   T *dA = nullptr, *dB = nullptr, *dC = nullptr;
-  int status = AM_OK;
   cudaError_t e = cudaSuccess;
   do {
-    if ((e = cudaMallocAsync(&dA, nA * sizeof(T), s_in)) != cudaSuccess || (e = cudaMallocAsync(&dB, nB * sizeof(T), s_in)) != cudaSuccess ||
-        (e = cudaMallocAsync(&dC, nC * sizeof(T), s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocAsync"); break; }
-    if ((e = cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+    if ((e = cudaMallocFromPoolAsync((void**)&dA, nA * sizeof(T), pool, s_in)) != cudaSuccess ||
+        (e = cudaMallocFromPoolAsync((void**)&dB, nB * sizeof(T), pool, s_in)) != cudaSuccess ||
+        (e = cudaMallocFromPoolAsync((void**)&dC, nC * sizeof(T), pool, s_in)) != cudaSuccess) { status = cuda_fail(e, "cudaMallocFromPoolAsync"); break; }
     if ((e = cudaMemcpyAsync(dB, B + loB, nB * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D B"); break; }
     if (nchunks == 1) {
       if ((e = cudaMemcpyAsync(dA, A + loA, nA * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A"); break; }
       if (beta != T(0) || nC != (size_t)(M * N)) {   // C is read, or the view has gaps that must survive the D2H copy
         if ((e = cudaMemcpyAsync(dC, C + loC, nC * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D C"); break; }
       }
-      status = device_gemm(s_in, M, N, K, alpha, dA - loA, rsA, csA, dB - loB, rsB, csB, beta, dC - loC, rsC, csC);
+      status = device_gemm(s_in, 0, M, N, K, alpha, dA - loA, rsA, csA, dB - loB, rsB, csB, beta, dC - loC, rsC, csC);
       if (status) break;
       if ((e = cudaMemcpyAsync(C + loC, dC, nC * sizeof(T), cudaMemcpyDeviceToHost, s_in)) != cudaSuccess) { status = cuda_fail(e, "D2H"); break; }
     } else {
-      cudaEventRecord(ev_alloc, s_in);                 // allocations are ordered on s_in
+      cudaEvent_t ev_alloc = hc.event();
+      if (!ev_alloc) { status = cuda_fail(cudaErrorMemoryAllocation, "event"); break; }
+      cudaEventRecord(ev_alloc, s_in);                 // allocations (and the B copy) are ordered on s_in
       cudaStreamWaitEvent(s_out, ev_alloc, 0);
       for (int j = 0; j < nchunks && !status; j++) {
         const int64_t r0 = (int64_t)j * chunk, rows = (M - r0 < chunk) ? M - r0 : chunk;
         const size_t a_elems = (size_t)((rows - 1) * rsA + (K - 1) * csA + 1);
-        const size_t c_elems = (size_t)((rows - 1) * rsC + (N - 1) * csC + 1);
-        if ((e = cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&ev_cmp[j], cudaEventDisableTiming)) != cudaSuccess) { status = cuda_fail(e, "event"); break; }
+        cudaEvent_t ev_in = hc.event(), ev_cmp = hc.event();
+        if (!ev_in || !ev_cmp) { status = cuda_fail(cudaErrorMemoryAllocation, "event"); break; }
         if ((e = cudaMemcpyAsync(dA + r0 * rsA, A + r0 * rsA, a_elems * sizeof(T), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { status = cuda_fail(e, "H2D A chunk"); break; }
-        cudaEventRecord(ev_in[j], s_in);
-        cudaStreamWaitEvent(s_cmp, ev_in[j], 0);       // (also orders after the B copy, issued earlier on s_in)
-        g_reuse_packed_b = (j > 0);
-        status = device_gemm(s_cmp, rows, N, K, alpha, dA + r0 * rsA, rsA, csA, dB - loB, rsB, csB, beta, dC + r0 * rsC, rsC, csC);
-        g_reuse_packed_b = false;
+        cudaEventRecord(ev_in, s_in);
+        cudaStreamWaitEvent(s_cmp, ev_in, 0);          // (also orders after the B copy, issued earlier on s_in)
+        status = device_gemm(s_cmp, j, rows, N, K, alpha, dA + r0 * rsA, rsA, csA, dB - loB, rsB, csB, beta, dC + r0 * rsC, rsC, csC);
         if (status) break;
-        cudaEventRecord(ev_cmp[j], s_cmp);
-        cudaStreamWaitEvent(s_out, ev_cmp[j], 0);
-        if ((e = cudaMemcpyAsync(C + r0 * rsC, dC + r0 * rsC, c_elems * sizeof(T), cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) { status = cuda_fail(e, "D2H C chunk"); break; }
+        cudaEventRecord(ev_cmp, s_cmp);
+        cudaStreamWaitEvent(s_out, ev_cmp, 0);
+        // exactly the N valid elements of each row (pitch rsC): gaps between the rows of a padded host C are not written
+        if ((e = cudaMemcpy2DAsync(C + r0 * rsC, (size_t)rsC * sizeof(T), dC + r0 * rsC, (size_t)rsC * sizeof(T), (size_t)N * sizeof(T),
+                                   (size_t)rows, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) { status = cuda_fail(e, "D2H C chunk"); break; }
       }
     }
   } while (0);
@@ -330,10 +369,6 @@ static int host_gemm(F&& device_gemm, int64_t M, int64_t N, int64_t K, T alpha, 
   if (dB) cudaFreeAsync(dB, s_in);
   if (dC) cudaFreeAsync(dC, s_in);
   cudaStreamSynchronize(s_in);
-  for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
-  for (auto ev : ev_cmp) if (ev) cudaEventDestroy(ev);
-  if (ev_alloc) cudaEventDestroy(ev_alloc);
-  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
   return status;
 }
 
@@ -361,6 +396,20 @@ int am_device_info(int* sms, int* major, int* minor) {
 
 int am_shutdown(void) {
   workspace_release_all();
+  host_pools_release();          // the private stream-ordered pools of the host-buffer entries go back to the driver
+  return AM_OK;
+}
+
+int am_set_tuning(const char* name, int value) {
+  const int k = tune_key(name);
+  if (k < 0) { set_last_error("am_set_tuning: unknown knob '%s'", name ? name : "(null)"); return AM_ERR_INVALID; }
+  g_tune[k].store(value);
+  return AM_OK;
+}
+int am_get_tuning(const char* name, int* value) {
+  const int k = tune_key(name);
+  if (k < 0 || !value) { set_last_error("am_get_tuning: unknown knob '%s'", name ? name : "(null)"); return AM_ERR_INVALID; }
+  *value = g_tune[k].load();
   return AM_OK;
 }
 
@@ -528,7 +577,7 @@ DEF_NN(f64, double)
   int am_host_gemm_strided_##SUF(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA, \
                                  const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) { \
     return host_gemm<T>(                                                                                        \
-        [](cudaStream_t st, int64_t m, int64_t n, int64_t k, T al, const T* a, int64_t ra, int64_t ca,          \
+        [](cudaStream_t st, int, int64_t m, int64_t n, int64_t k, T al, const T* a, int64_t ra, int64_t ca,     \
            const T* b, int64_t rb, int64_t cb, T be, T* c, int64_t rc_, int64_t cc) {                           \
           return am_gemm_strided_##SUF((am_stream_t)st, m, n, k, al, a, ra, ca, b, rb, cb, be, c, rc_, cc);     \
         },                                                                                                      \
@@ -537,18 +586,28 @@ DEF_NN(f64, double)
 int am_host_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA, int64_t csA,
                              const float* B, int64_t rsB, int64_t csB, float beta, float* C, int64_t rsC, int64_t csC) {
   // large row-major products on the tensor cores: K-pipelined uploads (see host_gemm_f32_kpipelined)
-  static const bool no_kpipe = getenv("AM_HOST_ROWCHUNKS") != nullptr;
   const int path = g_f32_path.load();
-  if (!no_kpipe && (path == AM_F32_AUTO || path == AM_F32_TC) && A && B && C && beta == 0.f && csA == 1 && csB == 1 && csC == 1 &&
+  if (!tuning(kTuneHostRowChunks) && (path == AM_F32_AUTO || path == AM_F32_TC) && A && B && C && beta == 0.f && csA == 1 && csB == 1 && csC == 1 &&
       rsA >= K && rsB >= N && rsC >= N && M >= 4096 && N >= 4096 && K >= 4096 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) &&
       gemm_f32_tc_available())
     return host_gemm_f32_kpipelined(M, N, K, alpha, A, rsA, B, rsB, C, rsC);
-  return host_gemm<float>(
-      [](cudaStream_t st, int64_t m, int64_t n, int64_t k, float al, const float* a, int64_t ra, int64_t ca, const float* b,
-         int64_t rb, int64_t cb, float be, float* c, int64_t rc_, int64_t cc) {
+  // row chunks: B is split/packed ONCE into an explicit handle by the first chunk that takes the tensor-core path and
+  // handed to the following chunks (no hidden "previous B" state in the GEMM)
+  void* hB = nullptr;
+  const bool tc_whole = (path == AM_F32_TC) || (path == AM_F32_AUTO && gemm_f32_tc_available() && M >= 256 && N >= 256 &&
+                                                K >= 256 && 2.0 * (double)M * (double)N * (double)K >= 3.0e9);
+  int rc = host_gemm<float>(
+      [&](cudaStream_t st, int, int64_t m, int64_t n, int64_t k, float al, const float* a, int64_t ra, int64_t ca, const float* b,
+          int64_t rb, int64_t cb, float be, float* c, int64_t rc_, int64_t cc) {
+        if (tc_whole && m >= 256 && gemm_f32_tc_available()) {
+          if (!hB) { int r = pack_f32(st, n, k, b, cb, rb, &hB); if (r) return r; }
+          return gemm_f32_tc(st, 2, m, n, k, al, a, ra, ca, b, rb, cb, be, c, rc_, cc, hB);
+        }
         return am_gemm_strided_f32((am_stream_t)st, m, n, k, al, a, ra, ca, b, rb, cb, be, c, rc_, cc);
       },
       M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  if (hB) packed_free_f32(hB);
+  return rc;
 }
 DEF_HOST(f64, double)
 DEF_HOST(i32, int32_t)

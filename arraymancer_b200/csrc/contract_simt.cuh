@@ -57,7 +57,23 @@ struct StridedLoader {
     *ok = s.ok && kt + s.k < Kend;
     return *ok ? s.ptr + kt * k_stride : p;
   }
+  // kStageVecMN (mn_stride == 1): V consecutive mn starting at the slot's mn, one k.  The slot only knows whether its
+  // FIRST mn is inside; the number of valid bytes is clamped against MN (the copy zero-fills the rest).
+  __device__ __forceinline__ const T* vec_addr(const Slot& s, int64_t kt) const {
+    return (s.ok && kt + s.k < Kend) ? s.ptr + kt * k_stride : p;
+  }
+  __device__ __forceinline__ int vec_bytes(const Slot& s, int64_t kt, int64_t) const {
+    if (!s.ok || kt + s.k >= Kend) return 0;
+    const int64_t mn = (s.ptr - p - (int64_t)s.k * k_stride);      // mn_stride == 1: element offset of the row start
+    const int64_t left = MN - mn;
+    return left >= (int64_t)(16 / sizeof(T)) ? 16 : (int)(left * (int64_t)sizeof(T));
+  }
 };
+
+// 16-byte cp.async with a runtime source size: bytes beyond src_bytes are zero-filled (src_bytes == 0: no read at all)
+__device__ __forceinline__ void cp_async_vec(uint32_t dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 
 template <class L, class = void> struct LoaderIsAsync { static constexpr bool value = false; };
 template <class L> struct LoaderIsAsync<L, typename std::enable_if<L::kAsync>::type> { static constexpr bool value = true; };
@@ -104,11 +120,29 @@ struct StridedEpilogue {   // gemm_ukernel_generic.nim:96-125 semantics on a str
 };
 
 // ---------------------------------------------------------------------------- mainloop
+// Staging modes of a StridedLoader operand (template parameters MA / MB):
+//   kStageScalar  one cp.async (LDGSTS) of sizeof(T) per element — any stride, sign or alignment;
+//   kStageVecMN   the operand's unit-stride dimension is mn (e.g. row-major B, column-major A): one 16-byte cp.async
+//                 moves V consecutive mn of one k straight into the [k][mn] shared tile (partial tails zero-filled by
+//                 the copy's src-size);
+//   kStageVecK    the unit-stride dimension is k (row-major A, transposed B): one 128-bit LDG fetches V consecutive k
+//                 of one mn into registers while the current tile is consumed, and V scalar STS transpose it into the
+//                 [k][mn] tile afterwards.
+// The vector modes need: unit stride along that dimension, the other stride a multiple of V, a 16-byte aligned base.
+enum : int { kStageScalar = 0, kStageVecMN = 1, kStageVecK = 2 };
+
 // grid = (ceil(N/BN), ceil(M/BM), splits); slice z covers k in [z*k_per_split, min(K, (z+1)*k_per_split)).
-template <class T, class Cfg, class LA, class LB, class Epi>
+// Batched = true: blockIdx.z is a batch index instead (no K split): operand / result pointers advance by the batch
+// strides bsA / bsB / bsC (StridedLoader / StridedEpilogue only).
+template <class T, class Cfg, class LA, class LB, class Epi, bool Batched = false, int MA = 0, int MB = 0>
 __global__ void __launch_bounds__(Cfg::NT)
-contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t k_per_split,
-                     int a_kfast, int b_kfast, const int* __restrict__ wide_flag = nullptr) {
+contract_simt_kernel(const LA la_, const LB lb_, const Epi epi_, int64_t K, int64_t k_per_split,
+                     int a_kfast, int b_kfast, const int* __restrict__ wide_flag = nullptr, int64_t bsA = 0,
+                     int64_t bsB = 0, int64_t bsC = 0) {
+  LA la = la_; LB lb = lb_; Epi epi = epi_;
+  if constexpr (Batched) {
+    la.p += (int64_t)blockIdx.z * bsA; lb.p += (int64_t)blockIdx.z * bsB; epi.C += (int64_t)blockIdx.z * bsC;
+  }
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN, V = Cfg::V;
   constexpr int TX = Cfg::TX, TY = Cfg::TY, NT = Cfg::NT, LDA = Cfg::LDA, LDB = Cfg::LDB;
   constexpr int EA = Cfg::EA, EB = Cfg::EB;
@@ -120,28 +154,37 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-  const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
-  const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  const int64_t kbeg = Batched ? 0 : (int64_t)blockIdx.z * k_per_split;
+  const int64_t kend = Batched ? K : ((kbeg + k_per_split < K) ? kbeg + k_per_split : K);
 
   // ---- staging slots: which (mn, k) of the tile each thread fetches, and where it lands
   const bool akf = LA::kMapping == 0 ? (a_kfast != 0) : (LA::kMapping == 2);
   const bool bkf = LB::kMapping == 0 ? (b_kfast != 0) : (LB::kMapping == 2);
-  typename LA::Slot sa[EA];
-  typename LB::Slot sb[EB];
-  int oa[EA], ob[EB];
+  // (scalar mode: EA / EB element slots; vector modes: EA/V / EB/V slots of V elements each)
+  constexpr int SA = MA == kStageScalar ? EA : (EA / V > 0 ? EA / V : 1);
+  constexpr int SB = MB == kStageScalar ? EB : (EB / V > 0 ? EB / V : 1);
+  static_assert(MA == kStageScalar || (EA % V == 0 && BK % V == 0 && BM % V == 0), "vector staging needs V | EA, BK, BM");
+  static_assert(MB == kStageScalar || (EB % V == 0 && BK % V == 0 && BN % V == 0), "vector staging needs V | EB, BK, BN");
+  typename LA::Slot sa[SA];
+  typename LB::Slot sb[SB];
+  int oa[SA], ob[SB];
 #pragma unroll
-  for (int i = 0; i < EA; i++) {
+  for (int i = 0; i < SA; i++) {
     const int idx = tid + i * NT;
-    const int mi = akf ? idx / BK : idx % BM;
-    const int ki = akf ? idx % BK : idx / BM;
+    int mi, ki;
+    if constexpr (MA == kStageVecMN) { mi = (idx % (BM / V)) * V; ki = idx / (BM / V); }
+    else if constexpr (MA == kStageVecK) { ki = (idx % (BK / V)) * V; mi = idx / (BK / V); }
+    else { mi = akf ? idx / BK : idx % BM; ki = akf ? idx % BK : idx / BM; }
     sa[i] = la.slot(m0 + mi, ki);
     oa[i] = ki * LDA + mi;
   }
 #pragma unroll
-  for (int i = 0; i < EB; i++) {
+  for (int i = 0; i < SB; i++) {
     const int idx = tid + i * NT;
-    const int ni = bkf ? idx / BK : idx % BN;
-    const int ki = bkf ? idx % BK : idx / BN;
+    int ni, ki;
+    if constexpr (MB == kStageVecMN) { ni = (idx % (BN / V)) * V; ki = idx / (BN / V); }
+    else if constexpr (MB == kStageVecK) { ki = (idx % (BK / V)) * V; ni = idx / (BK / V); }
+    else { ni = bkf ? idx / BK : idx % BN; ki = bkf ? idx % BK : idx / BN; }
     sb[i] = lb.slot(n0 + ni, ki);
     ob[i] = ki * LDB + ni;
   }
@@ -209,31 +252,85 @@ contract_simt_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int64_t
 
   if constexpr (LoaderIsAsync<LA>::value && LoaderIsAsync<LB>::value) {
     // ---- cp.async (LDGSTS) staging: tile t+1 streams into the other buffer while tile t is consumed; no
-    //      staging registers (the register-staged version had its loads sunk next to the STS by ptxas under the
-    //      128-register cap: 14 % of all stall samples on that one STS, profiles/r01_bringup.md)
+    //      staging registers (the register-staged scalar version had its loads sunk next to the STS by ptxas under
+    //      the 128-register cap: 14 % of all stall samples on that one STS, profiles/r01_bringup.md).  Operands in
+    //      kStageVecK mode go through ONE 128-bit register per V elements instead (see the enum above).
     const uint32_t as_base = (uint32_t)__cvta_generic_to_shared(&As[0][0][0]);
     const uint32_t bs_base = (uint32_t)__cvta_generic_to_shared(&Bs[0][0][0]);
-    auto issue = [&](int buf, int64_t kt) {
+    Vec va[MA == kStageVecK ? SA : 1], vb[MB == kStageVecK ? SB : 1];
+    // 128-bit load of V consecutive k of one mn; the (rare) vector that straddles Kend is assembled element-wise
+    auto ldg_vec = [&](const auto& L, const auto& sl, int64_t kt) -> Vec {
+      union { Vec q; T e[V]; } r;
+      if (sl.ok && kt + sl.k + V <= L.Kend) {
+        r.q = __ldg(reinterpret_cast<const Vec*>(sl.ptr + kt));          // k_stride == 1 in this mode
+      } else {
 #pragma unroll
-      for (int i = 0; i < EA; i++) {
-        bool ok;
-        const T* src = la.addr(sa[i], kt, &ok);
-        cp_async_zfill<(int)sizeof(T)>(as_base + (uint32_t)((buf * BK * LDA + oa[i]) * sizeof(T)), src, ok);
+        for (int v = 0; v < V; v++) r.e[v] = (sl.ok && kt + sl.k + v < L.Kend) ? sl.ptr[kt + v] : T(0);
       }
+      return r.q;
+    };
+    auto issue = [&](int buf, int64_t kt) {
+      if constexpr (MA == kStageScalar) {
 #pragma unroll
-      for (int i = 0; i < EB; i++) {
-        bool ok;
-        const T* src = lb.addr(sb[i], kt, &ok);
-        cp_async_zfill<(int)sizeof(T)>(bs_base + (uint32_t)((buf * BK * LDB + ob[i]) * sizeof(T)), src, ok);
+        for (int i = 0; i < SA; i++) {
+          bool ok;
+          const T* src = la.addr(sa[i], kt, &ok);
+          cp_async_zfill<(int)sizeof(T)>(as_base + (uint32_t)((buf * BK * LDA + oa[i]) * sizeof(T)), src, ok);
+        }
+      } else if constexpr (MA == kStageVecMN) {
+#pragma unroll
+        for (int i = 0; i < SA; i++)
+          cp_async_vec(as_base + (uint32_t)((buf * BK * LDA + oa[i]) * sizeof(T)), la.vec_addr(sa[i], kt), la.vec_bytes(sa[i], kt, m0));
+      } else {
+#pragma unroll
+        for (int i = 0; i < SA; i++) va[i] = ldg_vec(la, sa[i], kt);
+      }
+      if constexpr (MB == kStageScalar) {
+#pragma unroll
+        for (int i = 0; i < SB; i++) {
+          bool ok;
+          const T* src = lb.addr(sb[i], kt, &ok);
+          cp_async_zfill<(int)sizeof(T)>(bs_base + (uint32_t)((buf * BK * LDB + ob[i]) * sizeof(T)), src, ok);
+        }
+      } else if constexpr (MB == kStageVecMN) {
+#pragma unroll
+        for (int i = 0; i < SB; i++)
+          cp_async_vec(bs_base + (uint32_t)((buf * BK * LDB + ob[i]) * sizeof(T)), lb.vec_addr(sb[i], kt), lb.vec_bytes(sb[i], kt, n0));
+      } else {
+#pragma unroll
+        for (int i = 0; i < SB; i++) vb[i] = ldg_vec(lb, sb[i], kt);
       }
       cp_async_commit();
     };
-    if (ntiles > 0) issue(0, kbeg);
+    // registers of the kStageVecK operands -> [k][mn] tile (transposing scalar stores)
+    auto park = [&](int buf) {
+      if constexpr (MA == kStageVecK) {
+        T* a1 = &As[buf][0][0];
+#pragma unroll
+        for (int i = 0; i < SA; i++) {
+          union { Vec q; T e[V]; } r; r.q = va[i];
+#pragma unroll
+          for (int v = 0; v < V; v++) a1[oa[i] + v * LDA] = r.e[v];
+        }
+      }
+      if constexpr (MB == kStageVecK) {
+        T* b1 = &Bs[buf][0][0];
+#pragma unroll
+        for (int i = 0; i < SB; i++) {
+          union { Vec q; T e[V]; } r; r.q = vb[i];
+#pragma unroll
+          for (int v = 0; v < V; v++) b1[ob[i] + v * LDB] = r.e[v];
+        }
+      }
+    };
+    if (ntiles > 0) { issue(0, kbeg); park(0); }
     for (int64_t t = 0; t < ntiles; t++) {
       cp_async_wait_all();
       __syncthreads();          // tile t visible to all; everyone is done reading the other buffer (tile t-1)
-      if (t + 1 < ntiles) issue((int)((t + 1) & 1), kbeg + (t + 1) * BK);
+      const bool more = t + 1 < ntiles;
+      if (more) issue((int)((t + 1) & 1), kbeg + (t + 1) * BK);
       compute_tile((int)(t & 1));
+      if (more) park((int)((t + 1) & 1));
     }
   } else {
     T ra[EA], rb[EB];

@@ -11,6 +11,8 @@
 //       GEMM view: M = Cout, N = C*kH*kW (+1 ones-column = grad_bias, nnp_convolution.nim:94),
 //                  K = Nimg*Ho*Wo split over CTAs, fixed-order second pass (deterministic).
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 #include "contract_simt.cuh"
 #include "gemm_dispatch.h"
@@ -240,35 +242,45 @@ struct TableCache {
   int2 *tabF = nullptr, *tabD = nullptr, *tabW = nullptr;
   cudaEvent_t ready = nullptr;
 };
-static thread_local TableCache g_tab;
+// One cache entry per DEVICE, shared by all host threads and guarded by a mutex: the tables live in the per-device
+// workspace slot kWsConvTab, so the record of what that buffer holds must be per device too (a per-thread record let a
+// second thread overwrite the buffer while the first thread still believed its descriptor was cached).
+static TableCache g_tab[16];
+static std::mutex g_tab_mu;
 
 static int get_tables(cudaStream_t st, const am_conv2d_desc& d, const ConvGeom& g, int2** tabF, int2** tabD,
                       int2** tabW) {
   int dev = 0;
   AM_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) { set_last_error("conv: device index out of range"); return AM_ERR_INVALID; }
   const int64_t KD = g.Cout * g.kHkW;
   void* base = nullptr;
   const size_t nF = (size_t)round_up(g.Kc, 64), nD = (size_t)round_up(KD, 64);
   int rc = workspace(kWsConvTab, (nF + 2 * nD) * sizeof(int2), &base);
   if (rc) return rc;
   int2* f = (int2*)base; int2* dd = f + nF; int2* w = dd + nD;
-  const bool hit = g_tab.valid && g_tab.device == dev && g_tab.tabF == f &&
-                   memcmp(&g_tab.desc, &d, sizeof(d)) == 0;
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  TableCache& tc = g_tab[dev];
+  const bool hit = tc.valid && tc.tabF == f && memcmp(&tc.desc, &d, sizeof(d)) == 0;
   if (!hit) {
     const int64_t n = g.Kc > KD ? g.Kc : KD;
+    if (tc.ready) AM_CUDA_TRY(cudaStreamWaitEvent(st, tc.ready, 0));   // order after the previous build on another stream
     conv_build_tables<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, f, dd, w);
     g_launch_count++;
     AM_CUDA_TRY(cudaGetLastError());
-    if (!g_tab.ready) AM_CUDA_TRY(cudaEventCreateWithFlags(&g_tab.ready, cudaEventDisableTiming));
-    AM_CUDA_TRY(cudaEventRecord(g_tab.ready, st));
-    g_tab.desc = d; g_tab.device = dev; g_tab.valid = true; g_tab.tabF = f; g_tab.tabD = dd; g_tab.tabW = w;
+    if (!tc.ready) AM_CUDA_TRY(cudaEventCreateWithFlags(&tc.ready, cudaEventDisableTiming));
+    AM_CUDA_TRY(cudaEventRecord(tc.ready, st));
+    tc.desc = d; tc.device = dev; tc.valid = true; tc.tabF = f; tc.tabD = dd; tc.tabW = w;
   } else {
-    AM_CUDA_TRY(cudaStreamWaitEvent(st, g_tab.ready, 0));   // tables may have been built on another stream
+    AM_CUDA_TRY(cudaStreamWaitEvent(st, tc.ready, 0));   // tables may have been built on another stream
   }
   *tabF = f; *tabD = dd; *tabW = w;
   return AM_OK;
 }
-void conv_tables_invalidate() { g_tab.valid = false; }
+void conv_tables_invalidate() {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  for (auto& t : g_tab) t.valid = false;
+}
 
 // ------------------------------------------------------------------ launchers
 template <class T> struct ConvCfgs {
@@ -357,8 +369,10 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
                     const T* grad_output, T* grad_input, T* grad_kernel, T* grad_bias) {
   ConvGeom g;
   if (!make_geom(d, &g)) { set_last_error("conv2d_backward: invalid geometry"); return AM_ERR_INVALID; }
-  if (!grad_output || (grad_input && !kernel) || (grad_kernel && !input)) {
-    set_last_error("conv2d_backward: null pointer"); return AM_ERR_INVALID;
+  if (!grad_output || (grad_input && !kernel) || ((grad_kernel || grad_bias) && !input)) {
+    // the weight-gradient kernels produce grad_bias as an extra column of the same pass, so they read `input` too
+    set_last_error("conv2d_backward: null pointer (grad_kernel / grad_bias need `input`, grad_input needs `kernel`)");
+    return AM_ERR_INVALID;
   }
   constexpr int V = 16 / (int)sizeof(T);
   const int64_t NP = g.Nimg * g.HoWo, NQ = g.Nimg * g.HW, KD = g.Cout * g.kHkW;
@@ -369,7 +383,7 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
   bool dgrad_done = false;
   if constexpr (std::is_same<T, float>::value) {
     if (grad_input && g.Nimg > 0 && (tc_enabled() || auto_path())) {
-      static const bool gather_form = getenv("AM_CONVTC_DGRAD_GATHER") != nullptr;      // older gather-form kernel (comparison)
+      const bool gather_form = tuning(kTuneConvDgradGather) != 0;      // older gather-form kernel (comparison)
       if (gather_form && tc_enabled()) rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);
       else rc = conv2d_dgrad_col2im_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, !tc_enabled(), &dgrad_done);
       if (rc) return rc;

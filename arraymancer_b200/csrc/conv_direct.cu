@@ -196,7 +196,7 @@ static bool plan_direct(DirectArgs& a, int KW, int* ct_out, int* px_out, int* nt
   // {4,8}, 128..512 threads and 24..80 KB of staging on the LeNet layers (tools/gpu_bringup.py conv_sweep,
   // profiles/r01_bringup.md §4): the 4-channel tile won everywhere (more CTAs per SM hide the staging phases);
   // deep reductions (K' >= 256) want 512-thread CTAs (weight staging amortised), shallow ones 128.
-  auto envi = [](const char* n, int dflt) { const char* e = getenv(n); return (e && *e) ? atoi(e) : dflt; };   // tuning overrides
+  auto envi = [](const char*, int dflt) { return dflt; };   // (the round-1 sweep overrides are gone: the library reads no environment)
   const int CT = envi("AM_CONV_CT", 4);
   const int PX = envi("AM_CONV_PX", (a.WO % 8 == 0 || a.WO >= 32) ? 8 : 4);
   int CO_B = padded(a.CO, CT);

@@ -441,11 +441,9 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   ConvTcArgs a{};
   a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N; a.relu = v.relu;
   a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes;
-  static int groups_env = 0;
-  if (groups_env == 0) { const char* e = getenv("AM_CONVTC_GROUPS"); groups_env = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4; }
+  const int groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 4) ? tuning(kTuneConvTcGroups) : 4;
   a.groups = groups_env;
-  static int dbg_env = -1;
-  if (dbg_env < 0) { const char* e = getenv("AM_CONVTC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+  const int dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;
@@ -455,8 +453,7 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   }
   a.C = v.C; a.H = v.H; a.W = v.W; a.CO = v.CO; a.HO = v.HO; a.WO = v.WO; a.padH = v.padH; a.padW = v.padW; a.sH = v.sH; a.sW = v.sW;
   a.K = K; a.kblocks = nkb; a.NP = NP;
-  static int flush_env = -1;
-  if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
+  const int flush_env = tuning(kTuneTcFlushKb) > 0 ? tuning(kTuneTcFlushKb) : 2;
   a.flush_kb = flush_env;
   a.ntiles = (int)ceil_div(P, 128);
   const size_t smem = fixed + (size_t)stages * stage_bytes;

@@ -492,8 +492,8 @@ int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("conv dgrad tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AM_ERR_CUDA; }
   }
-  static int dbg_env = -1;
-  if (dbg_env < 0) { const char* e = getenv("AM_CONVTC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+  int dbg_env;
+  dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;
@@ -874,9 +874,9 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
   if ((int64_t)a.nslices > d.N) a.nslices = (int)d.N;
   if (a.nslices < 1) a.nslices = 1;
   a.spi = (HWo + 31) / 32;
-  static int flush_env = -1, groups_env = 0;
-  if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
-  if (groups_env == 0) { const char* e = getenv("AM_CONVTC_GROUPS"); groups_env = (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 3; }
+  int flush_env, groups_env;
+  flush_env = tuning(kTuneTcFlushKb) > 0 ? tuning(kTuneTcFlushKb) : 2;
+  groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 3) ? tuning(kTuneConvTcGroups) : 3;
   a.flush_st = flush_env;
   a.groups = groups_env > 3 ? 3 : groups_env;
   a.checked = (a.padH != 0 || a.padW != 0) ? 1 : 0;
@@ -895,8 +895,8 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
   a.part = (float*)part;
   const size_t smem = fixed + (size_t)SB * stage_bytes;
   AM_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static int dbg_env = -1;
-  if (dbg_env < 0) { const char* e = getenv("AM_CONVTC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+  int dbg_env;
+  dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;

@@ -10,6 +10,22 @@
 namespace am {
 
 extern std::atomic<int64_t> g_launch_count;
+
+// Explicit tuning knobs (am_set_tuning / am_get_tuning in the C ABI): process-wide atomics set by the caller; the
+// library reads NO environment variables.
+enum TuneKey : int {
+  kTuneTcFlushKb = 0,      // "tc_flush_kb": k-blocks (of 32) per tensor-core accumulation chain (default 2)
+  kTuneTcGroup,            // "tc_group": rasterisation group of the persistent GEMM (default 8; < 0: groups of N tiles)
+  kTuneTcSync,             // "tc_sync": per-wave grid barrier of the persistent GEMM (default 1)
+  kTunePackScalar,         // "pack_scalar": force the scalar split/pack kernel (default 0)
+  kTuneHostRowChunks,      // "host_rowchunks": host-buffer f32 GEMM uses row chunks only, no K pipeline (default 0)
+  kTuneConvTcGroups,       // "convtc_groups": gather-warp groups of the tcgen05 conv kernels (0 = kernel default)
+  kTuneConvTcDebug,        // "convtc_debug": per-role wait-cycle counters of the tcgen05 conv kernels (default 0)
+  kTuneConvDgradGather,    // "convtc_dgrad_gather": older gather-form tcgen05 dgrad kernel under AM_CONV_TC (default 0)
+  kTuneSimtVecLoad,        // "simt_vec_load": 128-bit global loads along a unit-stride operand dimension in the SIMT GEMM (default 1)
+  kTuneCount
+};
+int tuning(int key);
 extern std::atomic<int> g_conv_path;          // conv.cu: AM_CONV_AUTO / AM_CONV_GATHER
 
 // gemm_simt.cu — strided SIMT GEMM, any layout
@@ -17,11 +33,17 @@ template <class T>
 int gemm_simt(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA,
               const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC);
 
+// one launch for `batch` independent products (operand b at X + b*bsX), blockIdx.z = b
+template <class T>
+int gemm_simt_batched(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
+                      int64_t csA, int64_t bsA, const T* B, int64_t rsB, int64_t csB, int64_t bsB, T beta, T* C,
+                      int64_t rsC, int64_t csC, int64_t bsC);
+
 // gemm_f32_tc.cu — tcgen05 3xTF32 GEMM (split/pack pre-pass + TMA/UMMA mainloop)
 // cta_group: 1 or 2
 int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                 int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
-                int64_t rsC, int64_t csC);
+                int64_t rsC, int64_t csC, const void* prepackedB = nullptr);
 bool gemm_f32_tc_available();
 // pre-packed operands (two tf32 planes, K-major): pack once, multiply many
 int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, void** handle);
@@ -29,6 +51,7 @@ int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, 
 int64_t packed_floats_f32(int64_t R, int64_t K);
 int pack_f32_view(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, float* planes,
                   void** handle);
+int packed_wrap_f32(int64_t R, int64_t K, float* planes, void** handle);
 int packed_free_f32(void* handle);
 int gemm_packed_f32_bcast(cudaStream_t st, float alpha, const void* hA, const void* hB, int npeers, float* const* peers,
                           int self, int64_t rsC, int64_t csC);

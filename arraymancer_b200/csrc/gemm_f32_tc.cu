@@ -27,8 +27,6 @@
 
 namespace am {
 
-extern bool g_reuse_packed_b;   // am_api.cu: set while a host-buffer GEMM iterates over row chunks
-
 // ------------------------------------------------------------------ split / pack pre-pass
 // out planes: [Rpad][Kpad] row-major (K contiguous).  (r, k) of X at X[r*r_stride + k*k_stride].
 __global__ void __launch_bounds__(256)
@@ -257,6 +255,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
         uint32_t it = 0;
         unsigned long long expected = 0;      // cumulative arrivals the grid barrier must have seen
         int round = 0;
+        bool lockstep = true;                 // cleared by the first timeout: the CTAs are not all co-resident
         for (int tile = cluster_id; tile < ntiles; tile += nclusters, round++) {
           if (round > 0 && p.sync_counter != nullptr) {
             // grid barrier (bounded spin): every CTA that has a tile in this round arrives once
@@ -264,8 +263,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
             expected += (unsigned long long)CG * (unsigned)(rem < nclusters ? rem : nclusters);
             atomicAdd(p.sync_counter, 1u);
             const long long t0 = clock64();
-            while (*((volatile unsigned*)p.sync_counter) < (unsigned)expected) {
-              if (clock64() - t0 > 400000) break;           // ~0.2 ms: never deadlock if a CTA is not co-resident
+            while (lockstep && *((volatile unsigned*)p.sync_counter) < (unsigned)expected) {
+              // ~0.2 ms: never deadlock if a CTA is not co-resident (e.g. a communication kernel holds some SMs);
+              // after ONE timeout this CTA stops waiting for the rest of the launch (it still arrives, so the others'
+              // counts stay right) — the schedule degrades to the free-running one instead of paying 0.2 ms per wave
+              if (clock64() - t0 > 400000) { lockstep = false; break; }
               __nanosleep(64);
             }
           }
@@ -510,8 +512,7 @@ static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int6
   const bool kf = iabs64(k_stride) <= iabs64(r_stride);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && R % 4 == 0 && K % 4 == 0 && out->Rpad % 64 == 0 &&
                       (kf ? (k_stride == 1 && r_stride % 4 == 0) : (r_stride == 1 && k_stride % 4 == 0));
-  static const bool no_vec = getenv("AM_PACK_SCALAR") != nullptr;
-  if (vec_ok && !no_vec) {
+  if (vec_ok && !tuning(kTunePackScalar)) {
     // rows r >= R (padding) are produced as zeros by the bounds test; k in [K, Kpad) likewise (Kpad - K < 32, K % 4 == 0)
     split_pack_vec_kernel<<<dim3((unsigned)ceil_div(out->Kpad, 64), (unsigned)(out->Rpad / 64)), 256, 0, st>>>(
         X, R, K, r_stride, k_stride, out->hi, out->lo, out->Kpad, kf ? 1 : 0);
@@ -531,8 +532,7 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
                       float beta, float* C, int64_t strideP, int64_t strideQ, int npeers = 0, float* const* peers = nullptr,
                       int self = 0) {
   if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
-  static int flush_env = -1;
-  if (flush_env < 0) { const char* e = getenv("AM_TC_FLUSH_KB"); flush_env = (e && atoi(e) > 0) ? atoi(e) : 2; }
+  const int flush_env = tuning(kTuneTcFlushKb) > 0 ? tuning(kTuneTcFlushKb) : 2;
   const int bk = 32;
   CUtensorMap tms[4];
   int rc;
@@ -540,17 +540,14 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
       (rc = make_tmap(&tms[2], Q.hi, Q.Rpad, Q.Kpad, bk)) || (rc = make_tmap(&tms[3], Q.lo, Q.Rpad, Q.Kpad, bk)))
     return rc;
   TcArgs args;
-  static int group_env = 0;    // 0 = not read yet; > 0: groups of M-tiles (M fastest), < 0: groups of N-tiles (N fastest)
-  if (group_env == 0) { const char* e = getenv("AM_TC_GROUP"); group_env = (e && atoi(e) != 0) ? atoi(e) : 8; }
+  const int group_env = tuning(kTuneTcGroup) != 0 ? tuning(kTuneTcGroup) : 8;   // > 0: groups of M-tiles (M fastest), < 0: groups of N-tiles
   args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
   args.npeers = npeers; args.self = self;
   for (int g = 0; g < 8; g++) args.peer[g] = (g < npeers) ? peers[g] : nullptr;
   // grid-barrier counter of the persistent schedule: one slot of a small ring, zeroed in stream order
-  static int sync_env = -1;
-  if (sync_env < 0) { const char* e = getenv("AM_TC_SYNC"); sync_env = (e && e[0] == '0') ? 0 : 1; }
   args.sync_counter = nullptr;
-  if (sync_env) {
+  if (tuning(kTuneTcSync)) {
     static std::atomic<unsigned> ring{0};
     void* base = nullptr;
     if ((rc = workspace(kWsMisc, 64 * sizeof(int) + 1024, &base))) return rc;
@@ -567,9 +564,11 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
   return launch_tc<1>(st, tms, args);
 }
 
+// prepackedB != nullptr: B was split/packed by the caller (a handle from pack_f32 / pack_f32_view for B[K,N] in the
+// "b" role, i.e. rows = n) and is reused as is — only A is packed here (row chunks of one host-buffer product).
 int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                 int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
-                int64_t rsC, int64_t csC) {
+                int64_t rsC, int64_t csC, const void* prepackedB) {
   if (!gemm_f32_tc_available()) { set_last_error("tcgen05 path needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
   if (M >= (1ll << 31) - 1024 || N >= (1ll << 31) - 1024 || K >= (1ll << 31) - 64) { set_last_error("gemm_f32_tc: dimension too large"); return AM_ERR_INVALID; }
   // Operands in (panel-row stride, k stride) form: A panel rows = m, B panel rows = n.
@@ -578,17 +577,17 @@ int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K,
   void *wsA = nullptr, *wsB = nullptr;
   int rc = workspace(kWsSplitA, (size_t)(2 * pa.Rpad * pa.Kpad) * sizeof(float), &wsA);
   if (rc) return rc;
-  rc = workspace(kWsSplitB, (size_t)(2 * pb.Rpad * pb.Kpad) * sizeof(float), &wsB);
-  if (rc) return rc;
   pa.hi = (float*)wsA; pa.lo = pa.hi + pa.Rpad * pa.Kpad;
-  pb.hi = (float*)wsB; pb.lo = pb.hi + pb.Rpad * pb.Kpad;
-  // inside one am_host_gemm_strided_f32 call B is packed by the first row chunk and reused by the rest
-  static thread_local struct { const float* B; int64_t N, K, rs, cs; float* ws; } last_b = {nullptr, 0, 0, 0, 0, nullptr};
-  const bool reuse_b = g_reuse_packed_b && last_b.B == B && last_b.N == N && last_b.K == K && last_b.rs == rsB &&
-                       last_b.cs == csB && last_b.ws == pb.hi;
   if ((rc = pack_into(st, A, M, K, rsA, csA, &pa))) return rc;
-  if (!reuse_b && (rc = pack_into(st, B, N, K, csB, rsB, &pb))) return rc;
-  last_b = {B, N, K, rsB, csB, pb.hi};
+  if (prepackedB) {
+    pb = *(const PackedF32*)prepackedB;
+    if (pb.R != N || pb.K != K) { set_last_error("gemm_f32_tc: pre-packed B does not match N, K"); return AM_ERR_INVALID; }
+  } else {
+    rc = workspace(kWsSplitB, (size_t)(2 * pb.Rpad * pb.Kpad) * sizeof(float), &wsB);
+    if (rc) return rc;
+    pb.hi = (float*)wsB; pb.lo = pb.hi + pb.Rpad * pb.Kpad;
+    if ((rc = pack_into(st, B, N, K, csB, rsB, &pb))) return rc;
+  }
   // The epilogue's lanes run along the P rows (TMEM lanes): make that C's unit-stride dimension.
   // Column-major C (rs == 1, the CudaTensor default): P = A.  Row-major C: C^T = B^T A^T, P = B.
   if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, cta_group, pa, pb, alpha, beta, C, rsC, csC);
@@ -619,6 +618,12 @@ int pack_f32_view(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t
   int rc = pack_into(st, X, R, K, r_stride, k_stride, p);
   if (rc) { delete p; return rc; }
   *handle = p;
+  return AM_OK;
+}
+// handle over planes that already hold a packed operand (e.g. a K slice of B received from a peer GPU)
+int packed_wrap_f32(int64_t R, int64_t K, float* planes, void** handle) {
+  if (R <= 0 || K <= 0 || !handle || !planes) { set_last_error("packed_wrap_f32: bad argument"); return AM_ERR_INVALID; }
+  *handle = new PackedF32{planes, planes + pad_rows(R) * pad_k(K), R, K, pad_rows(R), pad_k(K), false};
   return AM_OK;
 }
 int repack_f32(cudaStream_t st, void* handle, const float* X, int64_t r_stride, int64_t k_stride) {

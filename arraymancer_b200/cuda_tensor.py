@@ -66,6 +66,29 @@ def _gemm_raw(suf, device, M, N, K, alpha, a, b, beta, c) -> None:
             b[0], b[1], b[2], ct(beta), c[0], c[1], c[2]))
 
 
+def gemm_strided_batched(alpha, A: torch.Tensor, B: torch.Tensor, beta, C: torch.Tensor) -> torch.Tensor:
+    """C[b] <- alpha*A[b]@B[b] + beta*C[b] for rank-3 CUDA views [batch, rows, cols] of any strides (a batch stride of 0,
+    e.g. an `expand`ed operand, shares that operand between the products): am_gemm_strided_batched_* — the device
+    counterpart of `cublas_gemmStridedBatched` (tensor/backend/cublas.nim:172-208)."""
+    if A.dim() != 3 or B.dim() != 3 or C.dim() != 3:
+        raise ValueError("gemm_strided_batched: operands must be rank-3 [batch, rows, cols]")
+    if A.dtype not in _SUFFIX or B.dtype != A.dtype or C.dtype != A.dtype:
+        raise TypeError("gemm_strided_batched: operands must share one of float32/float64/int32/int64")
+    nb, M, K = A.shape
+    nb2, K2, N = B.shape
+    if nb != nb2 or K != K2 or tuple(C.shape) != (nb, M, N):
+        raise IndexError(f"gemm_strided_batched: shape mismatch {tuple(A.shape)} * {tuple(B.shape)} -> {tuple(C.shape)}")
+    if not (A.is_cuda and B.is_cuda and C.is_cuda):
+        raise ValueError("gemm_strided_batched: operands must live on the GPU (no CPU fallback)")
+    suf = _SUFFIX[A.dtype]
+    ct = _capi.CTYPE[suf]
+    with torch.cuda.device(C.device):
+        _capi.check(getattr(_capi.lib(), f"am_gemm_strided_batched_{suf}")(
+            _stream_ptr(C), nb, M, N, K, ct(alpha), A.data_ptr(), A.stride(1), A.stride(2), A.stride(0),
+            B.data_ptr(), B.stride(1), B.stride(2), B.stride(0), ct(beta), C.data_ptr(), C.stride(1), C.stride(2), C.stride(0)))
+    return C
+
+
 def cublas_gemm(transa: int, transb: int, m: int, n: int, k: int, alpha, A: torch.Tensor, lda: int,
                 B: torch.Tensor, ldb: int, beta, C: torch.Tensor, ldc: int) -> None:
     """Column-major cuBLAS-shaped entry (tensor/backend/cublas.nim:142-170); A, B, C are flat
@@ -199,6 +222,8 @@ def matmul(a: CudaTensor, b: CudaTensor) -> CudaTensor:
         if a.shape[1] != b.shape[0]:
             raise IndexError(f"matmul: inner dimensions differ: {a.shape} * {b.shape}")   # check_matmat
         out = CudaTensor.new((a.shape[0], b.shape[1]), a.dtype, a.storage.device)
+        if a.shape[1] == 0:
+            out.storage.zero_()      # K == 0: the kernel leaves C untouched (gemm.nim:203); an empty sum is 0, like cuBLAS with beta = 0
         gemm(1, a, b, 0, out)
         return out
     if a.rank == 2 and b.rank == 1:
@@ -209,6 +234,8 @@ def matmul(a: CudaTensor, b: CudaTensor) -> CudaTensor:
         bv = CudaTensor(b.storage, (b.shape[0], 1), (b.strides[0], 1), b.offset)
         out = CudaTensor.new((a.shape[0],), a.dtype, a.storage.device)
         ov = CudaTensor(out.storage, (a.shape[0], 1), (1, a.shape[0]), 0)
+        if a.shape[1] == 0:
+            out.storage.zero_()
         gemm(1, a, bv, 0, ov)
         return out
     raise ValueError("Matrix-Matrix or Matrix-Vector multiplication valid only if first Tensor is a Matrix "

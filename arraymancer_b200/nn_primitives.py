@@ -42,18 +42,24 @@ def conv_out_dims(inp_shape, kernel_shape, padding=(0, 0), strides=(1, 1), dilat
 
 
 def _check_mem(*ts):
-    dt = None
+    """Returns (dtype suffix, all tensors dense NCHW?).  Non-dense views (transposed, sliced, Fortran-ordered ...) are
+    legal: they cross the boundary with their 4 element strides (am_conv2d_*_strided_*), as the reference builds its
+    descriptors from `t.strides` (nn_primitives/backend/cudnn.nim:59-75)."""
+    dt, dense = None, True
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise ValueError("conv2d: tensors must live on the GPU (no CPU fallback)")
-        if not t.is_contiguous():
-            raise ValueError("conv2d: tensors must be C-contiguous NCHW")
+        dense = dense and t.is_contiguous()
         dt = dt or t.dtype
         if t.dtype != dt or t.dtype not in _SUFFIX:
             raise TypeError("conv2d: tensors must share one of float32/float64/int32/int64")
-    return _SUFFIX[dt]
+    return _SUFFIX[dt], dense
+
+
+def _strides4(t):
+    return (ctypes.c_int64 * 4)(*[int(x) for x in t.stride()])
 
 
 def conv2d(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None = None,
@@ -70,13 +76,18 @@ def conv2d(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor | None 
         if bias.numel() != kernel.shape[0]:
             raise IndexError("conv2d: bias must have Cout elements ([Cout,1,1])")
         bias = bias.reshape(-1)
-    suf = _check_mem(input, kernel, bias)
+    suf, dense = _check_mem(input, kernel, bias)
     shape = conv_out_dims(input.shape, kernel.shape, padding, strides, dilation)
     if shape[2] <= 0 or shape[3] <= 0:
         raise ValueError("conv2d: kernel larger than the padded input")
     out = torch.empty(shape, dtype=input.dtype, device=input.device)
     with torch.cuda.device(input.device):
-        if activation is None:
+        if not dense:
+            _capi.check(getattr(_capi.lib(), f"am_conv2d_forward_strided_{suf}")(
+                _stream_ptr(input), ctypes.byref(d), input.data_ptr(), _strides4(input), kernel.data_ptr(), _strides4(kernel),
+                bias.data_ptr() if bias is not None else None, int(bias.stride(0)) if bias is not None else 1,
+                out.data_ptr(), None, _capi.ACT_RELU if activation else _capi.ACT_NONE))
+        elif activation is None:
             _capi.check(getattr(_capi.lib(), f"am_conv2d_forward_{suf}")(
                 _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(),
                 bias.data_ptr() if bias is not None else None, out.data_ptr()))
@@ -96,7 +107,7 @@ def conv2d_backward(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tenso
     d = _desc(input, kernel, padding, strides, dilation)
     if bias is not None and bias.numel() == 0:
         bias = None
-    suf = _check_mem(input, kernel, grad_output)
+    suf, dense = _check_mem(input, kernel, grad_output)
     want = conv_out_dims(input.shape, kernel.shape, padding, strides, dilation)
     if tuple(grad_output.shape) != tuple(want):
         raise IndexError(f"conv2d_backward: grad_output shape {tuple(grad_output.shape)} != {want}")
@@ -104,6 +115,13 @@ def conv2d_backward(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tenso
     gk = torch.empty_like(kernel) if need_kernel_grad else None
     gb = (torch.empty((kernel.shape[0], 1, 1), dtype=input.dtype, device=input.device)
           if (bias is not None and need_kernel_grad) else None)
+    if not dense:
+        with torch.cuda.device(input.device):
+            _capi.check(getattr(_capi.lib(), f"am_conv2d_backward_strided_{suf}")(
+                _stream_ptr(input), ctypes.byref(d), input.data_ptr(), _strides4(input), kernel.data_ptr(), _strides4(kernel),
+                grad_output.data_ptr(), _strides4(grad_output), gin.data_ptr() if gin is not None else None, None,
+                gk.data_ptr() if gk is not None else None, None, gb.data_ptr() if gb is not None else None, 1))
+        return gin, gk, gb
     with torch.cuda.device(input.device):
         _capi.check(getattr(_capi.lib(), f"am_conv2d_backward_{suf}")(
             _stream_ptr(input), ctypes.byref(d), input.data_ptr(), kernel.data_ptr(), grad_output.data_ptr(),

@@ -43,6 +43,17 @@ AM_API int am_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Frees the per-device workspace caches (split/packed operand panels, conv tables).
  * Reference scratch is per call (laser/.../gemm_tiling.nim:266-270,326); here it is cached. */
 AM_API int am_shutdown(void);
+/* Tuning knobs, set explicitly by the caller (process-wide atomics; the library reads NO environment variables):
+ *   "tc_flush_kb" (2)  k-blocks of 32 per tensor-core accumulation chain of the 3xTF32 kernels
+ *   "tc_group" (8)     rasterisation group of the persistent GEMM (< 0: groups of N tiles)
+ *   "tc_sync" (1)      per-wave grid barrier of the persistent GEMM
+ *   "pack_scalar" (0)  force the scalar split/pack kernel
+ *   "host_rowchunks" (0)  am_host_gemm_strided_f32 uses row chunks only (no K pipeline)
+ *   "convtc_groups" (0 = kernel default), "convtc_debug" (0), "convtc_dgrad_gather" (0): tcgen05 conv kernels
+ *   "simt_vec_load" (1)  128-bit global accesses along a unit-stride operand dimension in the SIMT GEMM
+ * Unknown names return AM_ERR_INVALID. */
+AM_API int am_set_tuning(const char* name, int value);
+AM_API int am_get_tuning(const char* name, int* value);
 
 /* ---- GEMM: mirror of laser gemm_strided ------------------------------------------------
  * Replaces: laser/primitives/matrix_multiplication/gemm.nim:192-201 (`gemm_strided[T]`, raw
@@ -120,6 +131,34 @@ AM_API int am_gemm_packed_f32_bcast(am_stream_t stream, float alpha, const am_pa
                                     const am_packed_f32* B, int npeers, float* const* peerC,
                                     int self_index, int64_t rowStrideC, int64_t colStrideC);
 AM_API int am_packed_free_f32(am_packed_f32* h);
+/* Packed operands in CALLER-OWNED device memory (the handle is only a descriptor; am_packed_free_f32 drops it and
+ * leaves the memory alone): am_packed_floats_f32(R, K) = floats a packed operand of R panel rows (M for an A, N for a
+ * B) and depth K occupies; am_pack_f32_{a,b}_into pack into `planes`; am_packed_wrap_f32 describes planes that already
+ * hold a packed operand of that shape — e.g. a K slice of B split/packed by another GPU and received over NVLink
+ * (the multi-GPU host-buffer GEMM exchanges packed K slices instead of uploading all of B on every GPU). */
+AM_API int64_t am_packed_floats_f32(int64_t R, int64_t K);
+AM_API int am_pack_f32_a_into(am_stream_t stream, int64_t M, int64_t K, const float* A, int64_t rowStrideA,
+                              int64_t colStrideA, float* planes, am_packed_f32** out);
+AM_API int am_pack_f32_b_into(am_stream_t stream, int64_t K, int64_t N, const float* B, int64_t rowStrideB,
+                              int64_t colStrideB, float* planes, am_packed_f32** out);
+AM_API int am_packed_wrap_f32(int64_t R, int64_t K, float* planes, am_packed_f32** out);
+
+/* ---- batched GEMM ----------------------------------------------------------------------------
+ * Replaces: tensor/backend/cublas.nim:172-208 `cublas_gemmStridedBatched` (declared, no caller yet) and serves the
+ * reference's "TODO: batch matmul" over the images of a conv (nn_primitives/fallback/conv.nim:99).
+ * For b in [0, batch): C_b <- alpha*A_b*B_b + beta*C_b with X_b = X + b*batchStrideX (elements; 0 = the operand is
+ * shared by all products), every product with the semantics of am_gemm_strided_*.  Small products share one launch
+ * (blockIdx.z = b); products that fill the chip on their own take the single-product kernels one after the other. */
+#define AM_DECL_BATCHED(SUF, T)                                                                                  \
+  AM_API int am_gemm_strided_batched_##SUF(am_stream_t stream, int64_t batch, int64_t M, int64_t N, int64_t K, T alpha, \
+                                           const T* A, int64_t rowStrideA, int64_t colStrideA, int64_t batchStrideA, \
+                                           const T* B, int64_t rowStrideB, int64_t colStrideB, int64_t batchStrideB, \
+                                           T beta, T* C, int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC);
+AM_DECL_BATCHED(f32, float)
+AM_DECL_BATCHED(f64, double)
+AM_DECL_BATCHED(i32, int32_t)
+AM_DECL_BATCHED(i64, int64_t)
+#undef AM_DECL_BATCHED
 
 /* ---- cuBLAS-shaped adapter -------------------------------------------------------------
  * Replaces: tensor/backend/cublas.nim:142-170 `cublas_gemm[T]` (column-major, op N/T), whose
@@ -181,6 +220,31 @@ AM_DECL_CONV(i32, int32_t)
 AM_DECL_CONV(i64, int64_t)
 #undef AM_DECL_CONV
 
+/* conv2d on STRIDED tensors: every tensor comes with its 4 element strides, the way the reference builds its
+ * descriptors from `t.strides[0..3]` (nn_primitives/backend/cudnn.nim:59-75), so views (transposed, sliced, Fortran-
+ * ordered grad_output ...) cross the boundary as they are — the Nim `conv2d_backward` no longer needs the
+ * `asContiguous` that is `{.error.}` on CUDA (nnp_conv2d_cudnn.nim:99-101).  A NULL strides pointer
+ * means dense NCHW; bias / grad_bias take one element stride (1 = dense [Cout]).  Dense tensors go straight to the
+ * kernels of am_conv2d_*; a non-dense tensor costs one extra pass over it (gathered into / scattered from a dense
+ * workspace copy by a coalescing copy kernel).  Same NULL-gradient convention as am_conv2d_backward_*. */
+#define AM_DECL_CONV_STRIDED(SUF, T)                                                                             \
+  AM_API int am_conv2d_forward_strided_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input,         \
+                                             const int64_t* input_strides, const T* kernel,                       \
+                                             const int64_t* kernel_strides, const T* bias, int64_t bias_stride,   \
+                                             T* output, const int64_t* output_strides, int activation);           \
+  AM_API int am_conv2d_backward_strided_##SUF(am_stream_t stream, const am_conv2d_desc* d, const T* input,        \
+                                              const int64_t* input_strides, const T* kernel,                      \
+                                              const int64_t* kernel_strides, const T* grad_output,                \
+                                              const int64_t* grad_output_strides, T* grad_input,                  \
+                                              const int64_t* grad_input_strides, T* grad_kernel,                  \
+                                              const int64_t* grad_kernel_strides, T* grad_bias,                   \
+                                              int64_t grad_bias_stride);
+AM_DECL_CONV_STRIDED(f32, float)
+AM_DECL_CONV_STRIDED(f64, double)
+AM_DECL_CONV_STRIDED(i32, int32_t)
+AM_DECL_CONV_STRIDED(i64, int64_t)
+#undef AM_DECL_CONV_STRIDED
+
 /* ---- host-buffer entry points (the reference-facing "plugin" call with HOST memory) ------
  * What `a.cuda * b.cuda` followed by `.cpu` does in the reference
  * (tensor/init_cuda.nim:23-59 + operators_blas_l2l3_cuda.nim:74-87): device buffers are
@@ -199,6 +263,12 @@ AM_API int am_host_gemm_strided_i32(int64_t M, int64_t N, int64_t K, int32_t alp
 AM_API int am_host_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t* A,
                                     int64_t rsA, int64_t csA, const int64_t* B, int64_t rsB,
                                     int64_t csB, int64_t beta, int64_t* C, int64_t rsC, int64_t csC);
+
+/* Pitched copy on `stream` (cudaMemcpy2DAsync): a column block / K slice of a row-major HOST matrix to or from device
+ * memory without staging.  Pitches and width in BYTES; kind: 1 = host->device, 2 = device->host, 3 = device->device
+ * (UVA: also peer-mapped memory of another GPU, moved by the copy engines over NVLink).  Host memory should be pinned. */
+AM_API int am_memcpy2d_async(am_stream_t stream, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                             int64_t width, int64_t rows, int kind);
 
 /* ---- LeNet companions: the HBM-bound operators between the contractions ------------
  * so that a forward + backward step of the reference's ex02_mnist network stays on the device.  Dense NCHW /

@@ -198,12 +198,16 @@ static inline void epilogue_edge(T alpha, const T (&AB)[MR][NR], T beta, MatrixV
   }
 }
 
-// gemm.nim:57-109 — macro kernel: jr (step NR) x ir (step MR).  The reference marks
-// jr as an OpenMP taskloop; every (ir,jr) tile is independent so the result does not
-// depend on it — here the ic loop carries the parallelism (gemm.nim:168-171).
+// gemm.nim:57-109 — macro kernel: jr (step NR) x ir (step MR).  Like the reference
+// (`for jr in ||(0, nc-1, NR, "taskloop")`, gemm.nim:82) the jr loop is an OpenMP taskloop:
+// the tasks a thread creates for its ic tile are also run by team threads that have no ic
+// tile left (they wait at the end of the parallel region, a task scheduling point), so a
+// problem with fewer ic tiles than threads still uses the whole team.  Every (ir,jr) tile
+// is independent, the result does not depend on the schedule.
 template <class T, int MR, int NR, bool FMA>
 static void gebp_mkernel(int64_t mc, int64_t nc, int64_t kc, T alpha, const T* packA, const T* packB, T beta,
                          MatrixView<T> mcncC) {
+#pragma omp taskloop default(shared)
   for (int64_t jr = 0; jr < nc; jr += NR) {
     const int64_t nr = std::min<int64_t>(nc - jr, NR);
     for (int64_t ir = 0; ir < mc; ir += MR) {
@@ -228,13 +232,16 @@ static void gemm_impl(int64_t M, int64_t N, int64_t K, T alpha, MatrixView<const
     const int64_t kc = std::min<int64_t>(K - pc, tiles.kc);
     pack_B_kc_nc<T, NR>(tiles.b, kc, nc, vB.stride(pc, 0));
     const T beta_pc = (pc == 0) ? beta : T(1);             // gemm.nim:166
-#pragma omp parallel for schedule(static) if (parallelize)
-    for (int64_t icb = 0; icb < tiles.ic_num_tasks; icb++) {
-      T* packA = tiles.a + icb * tiles.upanelA_size;
-      const int64_t ic = icb * tiles.mc;
-      const int64_t mc = std::min<int64_t>(M - ic, tiles.mc);
-      pack_A_mc_kc<T, MR>(packA, mc, kc, vA.stride(ic, pc));
-      gebp_mkernel<T, MR, NR, FMA>(mc, nc, kc, alpha, packA, tiles.b, beta_pc, vC.stride(ic, 0));
+#pragma omp parallel if (parallelize)                      // gemm.nim:168 omp_parallel_if(parallelize)
+    {
+#pragma omp for nowait                                     // gemm.nim:171 `omp for nowait` over the ic tiles
+      for (int64_t icb = 0; icb < tiles.ic_num_tasks; icb++) {
+        T* packA = tiles.a + icb * tiles.upanelA_size;
+        const int64_t ic = icb * tiles.mc;
+        const int64_t mc = std::min<int64_t>(M - ic, tiles.mc);
+        pack_A_mc_kc<T, MR>(packA, mc, kc, vA.stride(ic, pc));
+        gebp_mkernel<T, MR, NR, FMA>(mc, nc, kc, alpha, packA, tiles.b, beta_pc, vC.stride(ic, 0));
+      }
     }
   }
 }

@@ -68,6 +68,58 @@ def max_threads() -> int:
     return int(lib().oracle_max_threads())
 
 
+class _NativeGemm:
+    """The same restatement compiled `-march=native` (bench.py's CPU arm only): lets the `-d:avx512` tile shapes
+    (14x32 / 14x16, gemm_tiling.nim:89-109) run with real AVX-512 registers on hosts that have them."""
+
+    def __init__(self, cdll):
+        self._l = cdll
+        for suf, ct in _CT.items():
+            f = getattr(cdll, f"oracle_gemm_strided_{suf}")
+            f.argtypes = [ctypes.c_int64] * 3 + [ct, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_int64, ct, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+            f.restype = None
+
+    def gemm_strided(self, alpha, A, B, beta, C, variant: int = AVX512, threads: int = 0):
+        suf = _SUFFIX[A.dtype]
+        ct = _CT[suf]
+        (rsA, csA), (rsB, csB), (rsC, csC) = _estrides(A), _estrides(B), _estrides(C)
+        getattr(self._l, f"oracle_gemm_strided_{suf}")(A.shape[0], B.shape[1], A.shape[1], ct(alpha), A.ctypes.data, rsA, csA,
+                                                       B.ctypes.data, rsB, csB, ct(beta), C.ctypes.data, rsC, csC, variant, threads)
+        return C
+
+
+_native = False
+
+
+def native():
+    """Build (once, on the machine that runs the CPU arm) and load oracle/liblaser_oracle_native.so; None when the host
+    has no AVX-512 (the 14x32 tiles would only spill) or the build fails."""
+    global _native
+    if _native is not False:
+        return _native
+    _native = None
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    if " avx512f" not in flags:
+        return None
+    import hashlib
+    # -march=native code must never run on another CPU model: the file name carries a hash of this host's model + flags
+    ident = "".join(l for l in flags.splitlines() if l.startswith(("model name", "flags")))[:8192]
+    path = os.path.join(_HERE, f"liblaser_oracle_native_{hashlib.sha1(ident.encode()).hexdigest()[:10]}.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    deps = [os.path.join(_HERE, f) for f in ("oracle.cpp", "laser_gemm.hpp", "conv_oracle.hpp")]
+    if not os.path.exists(path) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in deps):
+        subprocess.run([cxx, "-O3", "-std=c++17", "-fopenmp", "-march=native", "-ffp-contract=off", "-fPIC", "-fvisibility=hidden",
+                        "-shared", "-o", path, src], check=True, env={k: v for k, v in os.environ.items() if k not in ("CXX", "CC")})
+    _native = _NativeGemm(ctypes.CDLL(path))
+    return _native
+
+
 def _estrides(a: np.ndarray):
     assert a.ndim == 2
     it = a.dtype.itemsize

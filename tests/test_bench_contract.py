@@ -29,6 +29,34 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["sample_rows"] == 64 and "jr task loop" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_default_sample_scales_with_threads():
+    """rows = 192 x threads (one mc tile per thread) unless --cpu-rows is given; OMP team = all host threads."""
+    p = _run(["--impl", "reference", "--size", "768", "--steps", "1", "--gpus", "1", "--no-cpu-avx512"])
+    assert p.returncode == 0, p.stderr[-500:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    cores = d["cpu_baseline"]["cores"]
+    assert cores == len(os.sched_getaffinity(0))
+    assert d["config"]["sample_rows"] == min(768, 192 * cores)
+
+
+def test_device_generator_matches_host_splitmix64():
+    import numpy as np
+    import torch
+    from tools import bench_configs as bc
+    from tests.conftest import splitmix64
+    z = bc._splitmix64_torch(42, 4096, "cpu").numpy().view(np.uint64)
+    assert np.array_equal(z, splitmix64(42, 4096)) and np.array_equal(z, bc.splitmix64_numpy(42, 4096))
+    m = bc.gen_matrix_chunked("u100", 37, 53, 42, "cpu", torch.int64).numpy()
+    want = ((splitmix64(42, 37 * 53) >> np.uint64(33)) % np.uint64(100)).astype(np.int64).reshape(37, 53)
+    assert np.array_equal(m, want)
+    f = bc.gen_matrix_chunked("u11", 5, 7, 1234, "cpu", torch.float32).numpy()
+    assert f.min() >= -1 and f.max() < 1
+    k = bc.kostya(6, "cpu").numpy()
+    i, j = np.arange(6.0)[:, None], np.arange(6.0)[None, :]
+    assert np.array_equal(k, (1.0 / 36) * (i - j) * (i + j))
 
 
 def test_reference_arm_other_ranks_stay_silent():

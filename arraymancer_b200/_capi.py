@@ -81,7 +81,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"am_conv2d_forward_act_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, ci]
         getattr(L, f"am_conv2d_backward_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, p]
         getattr(L, f"am_conv2d_forward_strided_{s}").argtypes = [p, ctypes.POINTER(ConvDesc), p, p, p, p, p, i64, p, p, ci]
-        getattr(L, f"am_conv2d_backward_strided_{s}").argtypes = [p, ctypes.POINTER(ConvDesc)] + [p] * 12 + [i64]
+        getattr(L, f"am_conv2d_backward_strided_{s}").argtypes = [p, ctypes.POINTER(ConvDesc)] + [p] * 11 + [i64]
         getattr(L, f"am_gemm_strided_batched_{s}").argtypes = [p, i64, i64, i64, i64, ct, p, i64, i64, i64, p, i64, i64, i64,
                                                                ct, p, i64, i64, i64]
     f = ctypes.c_float

@@ -111,8 +111,9 @@ def conv2d_backward(input: torch.Tensor, kernel: torch.Tensor, bias: torch.Tenso
     want = conv_out_dims(input.shape, kernel.shape, padding, strides, dilation)
     if tuple(grad_output.shape) != tuple(want):
         raise IndexError(f"conv2d_backward: grad_output shape {tuple(grad_output.shape)} != {want}")
-    gin = torch.empty_like(input) if need_input_grad else None
-    gk = torch.empty_like(kernel) if need_kernel_grad else None
+    # fresh gradients are dense NCHW whatever the layout of the operands they belong to
+    gin = torch.empty(input.shape, dtype=input.dtype, device=input.device) if need_input_grad else None
+    gk = torch.empty(kernel.shape, dtype=kernel.dtype, device=kernel.device) if need_kernel_grad else None
     gb = (torch.empty((kernel.shape[0], 1, 1), dtype=input.dtype, device=input.device)
           if (bias is not None and need_kernel_grad) else None)
     if not dense:

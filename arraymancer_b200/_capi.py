@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = (
     ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path", "am_set_conv_path",
      "am_cublas_gemm_f32", "am_cublas_gemm_f64", "am_pack_f32_a", "am_pack_f32_b", "am_repack_f32_a",
      "am_repack_f32_b", "am_gemm_packed_f32", "am_gemm_packed_f32_bcast", "am_packed_free_f32", "am_conv2d_out_dims", "am_kernel_launch_count", "am_microbench",
-     "am_set_tuning", "am_get_tuning", "am_memcpy2d_async", "am_packed_floats_f32", "am_pack_f32_a_into", "am_pack_f32_b_into", "am_packed_wrap_f32"]
+     "am_set_tuning", "am_get_tuning", "am_memcpy2d_async", "am_mg_init", "am_mg_destroy", "am_mg_device_count",
+     "am_mg_stream", "am_mg_rows", "am_mg_synchronize", "am_mg_host_gemm_f32", "am_packed_floats_f32", "am_pack_f32_a_into", "am_pack_f32_b_into", "am_packed_wrap_f32"]
     + [f"am_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_host_gemm_strided_{s}" for s in SUFFIXES]
     + [f"am_conv2d_forward_{s}" for s in SUFFIXES]
@@ -34,6 +35,7 @@ EXPORTED_SYMBOLS = (
     + [f"am_conv2d_forward_strided_{s}" for s in SUFFIXES]
     + [f"am_conv2d_backward_strided_{s}" for s in SUFFIXES]
     + [f"am_gemm_strided_batched_{s}" for s in SUFFIXES]
+    + [f"am_mg_gemm_rowsharded_{s}" for s in SUFFIXES]
     + [f"am_{op}_{s}" for s in ("f32", "f64") for op in NN_OPS]
 )
 
@@ -97,6 +99,16 @@ def lib() -> ctypes.CDLL:
     L.am_pack_f32_a_into.argtypes = [p, i64, i64, p, i64, i64, p, ctypes.POINTER(p)]
     L.am_pack_f32_b_into.argtypes = [p, i64, i64, p, i64, i64, p, ctypes.POINTER(p)]
     L.am_packed_wrap_f32.argtypes = [i64, i64, p, ctypes.POINTER(p)]
+    L.am_mg_init.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(p)]
+    L.am_mg_destroy.argtypes = [p]
+    L.am_mg_device_count.argtypes = [p]
+    L.am_mg_stream.argtypes = [p, ci]
+    L.am_mg_stream.restype = p
+    L.am_mg_rows.argtypes = [p, i64, ci, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.am_mg_synchronize.argtypes = [p]
+    L.am_mg_host_gemm_f32.argtypes = [p, i64, i64, i64, f, p, i64, p, i64, p, i64]
+    for s in SUFFIXES:
+        getattr(L, f"am_mg_gemm_rowsharded_{s}").argtypes = [p, i64, i64, i64, CTYPE[s], p, i64, p, i64, p, i64]
     L.am_memcpy2d_async.argtypes = [p, p, i64, p, i64, i64, i64, ci]
     L.am_set_tuning.argtypes = [ctypes.c_char_p, ci]
     L.am_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(ci)]

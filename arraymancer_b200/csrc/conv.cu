@@ -327,6 +327,12 @@ int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t
                                const float* kernel, float* grad_input, bool only_if_fast, bool* done);
 int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
                         const float* grad_output, float** part_out, int* groups_out, bool* done);
+// conv_c1.cu: single-input-channel fused kernels (LeNet cv1 class); *done == false -> next path
+int conv2d_forward_c1_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                          const float* kernel, const float* bias, float* output, int act, bool* done);
+int conv2d_backward_c1_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, int64_t Wo, const float* input,
+                           const float* kernel, const float* grad_output, float* grad_input, float* grad_kernel,
+                           float* grad_bias, bool* done);
 std::atomic<int> g_conv_path{AM_CONV_AUTO};
 static bool direct_enabled() { return g_conv_path.load() != AM_CONV_GATHER; }
 static bool tc_enabled() { return g_conv_path.load() == AM_CONV_TC; }
@@ -340,6 +346,11 @@ int conv2d_forward(cudaStream_t st, const am_conv2d_desc& d, const T* input, con
   if (g.Nimg == 0) return AM_OK;
   if (!input || !kernel || !output) { set_last_error("conv2d_forward: null pointer"); return AM_ERR_INVALID; }
   if constexpr (std::is_same<T, float>::value) {
+    if (direct_enabled() && !tc_enabled()) {          // C = 1: the fused HBM-bound kernel (AUTO and DIRECT)
+      bool done = false;
+      int rcd = conv2d_forward_c1_f32(st, d, g.Ho, g.Wo, input, kernel, bias, output, act, &done);
+      if (rcd || done) return rcd;
+    }
     // AUTO: the tcgen05 implicit GEMM pays once the GEMM is wide and deep enough (measured: LeNet cv2 yes, cv1 no)
     if (tc_enabled() || (auto_path() && d.Cout >= 32 && g.Kc >= 128)) {
       bool done = false;
@@ -382,6 +393,12 @@ int conv2d_backward(cudaStream_t st, const am_conv2d_desc& d, const T* input, co
 
   bool dgrad_done = false;
   if constexpr (std::is_same<T, float>::value) {
+    if (g.Nimg > 0 && direct_enabled() && !tc_enabled() && (grad_input || grad_kernel || grad_bias)) {
+      // C = 1: data, weight and bias gradients from ONE pass over grad_output
+      bool done = false;
+      rc = conv2d_backward_c1_f32(st, d, g.Ho, g.Wo, input, kernel, grad_output, grad_input, grad_kernel, grad_bias, &done);
+      if (rc || done) return rc;
+    }
     if (grad_input && g.Nimg > 0 && (tc_enabled() || auto_path())) {
       const bool gather_form = tuning(kTuneConvDgradGather) != 0;      // older gather-form kernel (comparison)
       if (gather_form && tc_enabled()) rc = conv2d_dgrad_tc_f32(st, d, g.Ho, g.Wo, grad_output, kernel, grad_input, &dgrad_done);

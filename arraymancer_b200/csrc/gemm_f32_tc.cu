@@ -474,6 +474,21 @@ static int make_tmap(CUtensorMap* tm, float* base, int64_t rows, int64_t kpad, i
   return AM_OK;
 }
 
+// Dense (unswizzled) float32 tensor map of rank 2..4 for the staging loads of the conv kernels: dims / box innermost
+// first, strides_bytes[i] = byte stride of dimension i+1 (multiples of 16), zero fill outside the tensor.
+int make_tmap_f32_nd(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  if (!gemm_f32_tc_available()) { set_last_error("TMA needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1u; }
+  for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r); return AM_ERR_CUDA; }
+  return AM_OK;
+}
+
 template <int CG>
 static int launch_tc(cudaStream_t st, const CUtensorMap* tms, const TcArgs& args) {
   using Cfg = TcCfg<CG>;

@@ -270,6 +270,39 @@ AM_API int am_host_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alp
 AM_API int am_memcpy2d_async(am_stream_t stream, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                              int64_t width, int64_t rows, int kind);
 
+/* ---- multi-GPU (one host process drives the GPUs of a box) ------------------------------------------------
+ * The reference has no multi-device code and never calls cudaSetDevice; these entries manage the devices
+ * themselves and restore the caller's current device before returning (last row).  am_mg_init enables peer
+ * access between the listed devices (NULL = 0..ndev-1; 1 <= ndev <= 8) and creates the context's streams.
+ * Row-sharded GEMM: GPU g owns the contiguous rows [row0_g, row0_g + rows_g) of A and of C as reported by
+ * am_mg_rows(ctx, M, g, ...); A_local[g] points at ITS rows (rows_g x K, row pitch ldA) in GPU g's memory, B[g] at GPU
+ * g's replica of B (K x N, pitch ldB), C[g] at GPU g's buffer for the WHOLE result (M x N, pitch ldC).  After the call
+ * (asynchronous: am_mg_synchronize, or enqueue more work on am_mg_stream(ctx, g)) every C[g] holds alpha*A*B.
+ *   f32: the tcgen05 GEMM of every GPU stores its tiles into every GPU's copy of C from its epilogue, over NVLink
+ *        (peer-mapped pointers): product and all-gather are one kernel;
+ *   f64 / i32 / i64: row chunks, each pushed to the peers by the copy engines while the next chunk computes.
+ * No K split: integers stay bit-exact, floats are exactly the single-GPU kernels' results.
+ * am_mg_host_gemm_f32: A, B, C in HOST memory (row-major, pinned for speed); GPU g uploads its rows of A and only a
+ * 1/ndev share of B, the shares are exchanged between the GPUs; synchronous. */
+typedef struct am_mg_ctx am_mg_ctx;
+AM_API int am_mg_init(int ndev, const int* devices, am_mg_ctx** out);
+AM_API int am_mg_destroy(am_mg_ctx* ctx);
+AM_API int am_mg_device_count(const am_mg_ctx* ctx);
+AM_API void* am_mg_stream(const am_mg_ctx* ctx, int g);
+AM_API int am_mg_rows(const am_mg_ctx* ctx, int64_t M, int g, int64_t* row0, int64_t* rows);
+AM_API int am_mg_synchronize(am_mg_ctx* ctx);
+#define AM_DECL_MG(SUF, T)                                                                                        \
+  AM_API int am_mg_gemm_rowsharded_##SUF(am_mg_ctx* ctx, int64_t M, int64_t N, int64_t K, T alpha,                 \
+                                         const T* const* A_local, int64_t ldA, const T* const* B, int64_t ldB,     \
+                                         T* const* C, int64_t ldC);
+AM_DECL_MG(f32, float)
+AM_DECL_MG(f64, double)
+AM_DECL_MG(i32, int32_t)
+AM_DECL_MG(i64, int64_t)
+#undef AM_DECL_MG
+AM_API int am_mg_host_gemm_f32(am_mg_ctx* ctx, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
+                               const float* B, int64_t ldB, float* C, int64_t ldC);
+
 /* ---- LeNet companions: the HBM-bound operators between the contractions ------------
  * so that a forward + backward step of the reference's ex02_mnist network stays on the device.  Dense NCHW /
  * row-major device buffers, outputs pre-allocated by the caller, asynchronous on `stream`, deterministic.

@@ -23,6 +23,7 @@ def _header_symbols():
         names.add(f"am_conv2d_forward_strided_{suf}")            # AM_DECL_CONV_STRIDED(SUF, T)
         names.add(f"am_conv2d_backward_strided_{suf}")
         names.add(f"am_gemm_strided_batched_{suf}")              # AM_DECL_BATCHED(SUF, T)
+        names.add(f"am_mg_gemm_rowsharded_{suf}")                # AM_DECL_MG(SUF, T)
     for suf in ("f32", "f64"):                                   # AM_DECL_NN(SUF, T)
         for op in _capi.NN_OPS:
             names.add(f"am_{op}_{suf}")

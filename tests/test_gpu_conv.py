@@ -96,6 +96,13 @@ CASES = [  # input, kernel, padding, stride, dilation
     ((3, 6, 8, 8), (64, 6, 3, 3), (1, 1), (1, 1), (1, 1)),         # 64 output channels: full tensor-core N, padded taps
     ((2, 40, 10, 10), (33, 40, 3, 3), (0, 0), (1, 1), (1, 1)),     # 360 GEMM rows: several 128-row chunks
     ((4, 8, 9, 9), (16, 8, 2, 2), (0, 1), (1, 2), (1, 1)),         # even kernel, mixed stride, one-sided reach
+    # single input channel (conv_c1.cu fused kernels): 'same' 3x3, odd widths (scalar staging / stores), odd Cout,
+    # padded 5x5, more images than resident CTAs would hold at once
+    ((5, 1, 12, 12), (7, 1, 3, 3), (1, 1), (1, 1), (1, 1)),
+    ((3, 1, 13, 11), (20, 1, 5, 5), (0, 0), (1, 1), (1, 1)),
+    ((4, 1, 10, 9), (5, 1, 5, 5), (2, 2), (1, 1), (1, 1)),
+    ((700, 1, 8, 8), (3, 1, 3, 3), (0, 0), (1, 1), (1, 1)),
+    ((2, 1, 28, 28), (20, 1, 5, 5), (4, 4), (1, 1), (1, 1)),       # padding 4 = kW - 1: full correlation
 ]
 
 

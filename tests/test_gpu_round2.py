@@ -299,3 +299,49 @@ def test_tuning_knobs(am):
 def test_matmul_k_zero_returns_zeros(am):
     a = am.cuda(np.zeros((4, 0), np.float32)); b = am.cuda(np.zeros((0, 3), np.float32))
     assert np.array_equal((a * b).cpu(), np.zeros((4, 3), np.float32))
+
+
+# ---------------------------------------------------------------- single-process multi-GPU C entries (am_mg_*)
+def _mg_devices():
+    n = torch.cuda.device_count()
+    return [[0], [0, 0], [0, 0, 0]] + ([list(range(n))] if n > 1 else [])
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "i64", "i32"])
+def test_mg_gemm_rowsharded(am, oracle, dt):
+    """am_mg_gemm_rowsharded_*: every GPU of the context ends with the whole C.  On a one-GPU box the context lists
+    device 0 several times (the ranks then share the GPU): the row partition, the peer stores of the fused float32
+    epilogue and the copy-engine pushes of the other dtypes run exactly as across GPUs."""
+    from arraymancer_b200.multi_gpu import MgContext
+    cur = torch.cuda.current_device()
+    for devs in _mg_devices():
+        ctx = MgContext(devs)
+        for (M, N, K) in [(1100, 520, 300), (37, 29, 150)]:
+            a, b = rand((M, K), dt, 61), rand((K, N), dt, 62)
+            want = oracle.matmul(a, b)
+            A_local, Bs, Cs = [], [], []
+            for g, d in enumerate(devs):
+                r0, n = ctx.rows(M, g)
+                A_local.append(torch.from_numpy(np.ascontiguousarray(a[r0:r0 + n])).to(f"cuda:{d}"))
+                Bs.append(torch.from_numpy(b).to(f"cuda:{d}"))
+                Cs.append(torch.full((M, N), -7, dtype=TDT[dt], device=f"cuda:{d}"))
+            assert sum(ctx.rows(M, g)[1] for g in range(len(devs))) == M
+            ctx.gemm_rowsharded(1, A_local, Bs, Cs)
+            ctx.synchronize()
+            for g in range(len(devs)):
+                _assert_same(dt, Cs[g].cpu().numpy(), want, ("mg", devs, g, M, N, K))
+        ctx.close()
+    assert torch.cuda.current_device() == cur          # the caller's device is restored
+
+
+def test_mg_host_gemm_f32(am, oracle):
+    from arraymancer_b200.multi_gpu import MgContext
+    for devs in _mg_devices():
+        ctx = MgContext(devs)
+        M, N, K = 1300, 640, 520
+        a, b = rand((M, K), "f32", 71), rand((K, N), "f32", 72)
+        A, B = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        C = torch.empty((M, N), dtype=torch.float32).pin_memory()
+        ctx.host_gemm_f32(1.0, A, B, C)
+        assert rel_fro(C.numpy(), oracle.matmul(a, b)) <= F32_TOL, devs
+        ctx.close()

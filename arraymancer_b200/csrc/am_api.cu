@@ -81,9 +81,9 @@ static std::atomic<int> g_f32_path{AM_F32_AUTO};
 static std::atomic<int> g_f64_path{AM_F64_AUTO};
 
 // ------------------------------------------------------------------ explicit tuning knobs (no environment variables)
-static std::atomic<int> g_tune[kTuneCount] = {{2}, {8}, {1}, {0}, {0}, {0}, {0}, {0}, {1}};
+static std::atomic<int> g_tune[kTuneCount] = {{2}, {8}, {1}, {0}, {0}, {0}, {0}, {0}, {1}, {1}};
 static const char* const kTuneNames[kTuneCount] = {"tc_flush_kb", "tc_group", "tc_sync", "pack_scalar", "host_rowchunks",
-                                                   "convtc_groups", "convtc_debug", "convtc_dgrad_gather", "simt_vec_load"};
+                                                   "convtc_groups", "convtc_debug", "convtc_dgrad_gather", "simt_vec_load", "dmma_tma"};
 int tuning(int key) { return (key >= 0 && key < kTuneCount) ? g_tune[key].load(std::memory_order_relaxed) : 0; }
 static int tune_key(const char* name) {
   if (!name) return -1;
@@ -163,22 +163,42 @@ static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, const T*
   return AM_OK;
 }
 
-// f32: tcgen05 3xTF32 when the shape fills tensor tiles, exact FFMA kernel otherwise.
-static int gemm_f32_dispatch(cudaStream_t st, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
-                             int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta,
-                             float* C, int64_t rsC, int64_t csC) {
+// f32: tcgen05 3xTF32 when the shape fills tensor tiles, the DRAM-streaming kernel for skinny products, exact FFMA kernel
+// otherwise.  bias_col (nullable): the linear layer's bias, fused into the epilogue of whichever kernel runs.
+int gemm_dispatch_f32(cudaStream_t st, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA, int64_t csA,
+                      const float* B, int64_t rsB, int64_t csB, float beta, float* C, int64_t rsC, int64_t csC, const float* bias_col) {
   const int path = g_f32_path.load();
-  if (path == AM_F32_TC) return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
-  if (path == AM_F32_TC_1CTA) return gemm_f32_tc(st, 1, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  if (path == AM_F32_TC) return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr, bias_col);
+  if (path == AM_F32_TC_1CTA) return gemm_f32_tc(st, 1, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr, bias_col);
   if (path == AM_F32_AUTO && gemm_f32_tc_available()) {
     // worth it once K amortises the split/pack pre-pass (an extra pass over A and B) and there are a few output
     // tiles: measured crossover vs the SIMT kernel is around 3 GFLOP (LeNet's 4096x800x500 linear layer: 0.084 vs
     // 0.137 ms forward, 0.29 vs 0.385 ms backward; profiles/r01_bringup.md)
     const double flops = 2.0 * (double)M * (double)N * (double)K;
     if (M >= 256 && N >= 256 && K >= 256 && flops >= 3.0e9)
-      return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+      return gemm_f32_tc(st, 2, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr, bias_col);
   }
-  return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  if (path == AM_F32_AUTO && !bias_col) {
+    bool done = false;
+    int rc = gemm_skinny<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, &done);
+    if (rc || done) return rc;
+  }
+  return gemm_simt<float>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, bias_col);
+}
+
+int gemm_dispatch_f64(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t rsA, int64_t csA,
+                      const double* B, int64_t rsB, int64_t csB, double beta, double* C, int64_t rsC, int64_t csC, const double* bias_col) {
+  const int path = g_f64_path.load();
+  if (path == AM_F64_AUTO && !bias_col) {
+    bool done = false;
+    int rc = gemm_skinny<double>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, &done);
+    if (rc || done) return rc;
+  }
+  // DMMA kernel has one 128x128 tile shape: use it once those tiles cover most of the chip
+  const bool big = ceil_div(M, 128) * ceil_div(N, 128) >= (2 * (int64_t)sm_count()) / 3;
+  if (path == AM_F64_DMMA || (path == AM_F64_AUTO && big))
+    return gemm_f64_dmma(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, bias_col);
+  return gemm_simt<double>(st, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, bias_col);
 }
 
 
@@ -429,7 +449,7 @@ int am_gemm_strided_f32(am_stream_t s, int64_t M, int64_t N, int64_t K, float al
   int rc = check_gemm_args(M, N, K, A, B, C);
   if (rc == -1) return AM_OK;
   if (rc) return rc;
-  return gemm_f32_dispatch((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  return gemm_dispatch_f32((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr);
 }
 
 #define DEF_GEMM_SIMT(SUF, T)                                                                                  \
@@ -439,6 +459,9 @@ int am_gemm_strided_f32(am_stream_t s, int64_t M, int64_t N, int64_t K, float al
     int rc = check_gemm_args(M, N, K, A, B, C);                                                                 \
     if (rc == -1) return AM_OK;                                                                                 \
     if (rc) return rc;                                                                                          \
+    bool done = false;                                                                                          \
+    rc = gemm_skinny<T>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, &done);   \
+    if (rc || done) return rc;                                                                                  \
     return gemm_simt<T>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);          \
   }
 int am_set_f64_path(int path) {
@@ -454,12 +477,7 @@ int am_gemm_strided_f64(am_stream_t s, int64_t M, int64_t N, int64_t K, double a
   int rc = check_gemm_args(M, N, K, A, B, C);
   if (rc == -1) return AM_OK;
   if (rc) return rc;
-  const int path = g_f64_path.load();
-  // DMMA kernel has one 128x128 tile shape: use it once those tiles cover most of the chip
-  const bool big = ceil_div(M, 128) * ceil_div(N, 128) >= (2 * (int64_t)sm_count()) / 3;
-  if (path == AM_F64_DMMA || (path == AM_F64_AUTO && big))
-    return gemm_f64_dmma((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
-  return gemm_simt<double>((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  return gemm_dispatch_f64((cudaStream_t)s, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr);
 }
 DEF_GEMM_SIMT(i32, int32_t)
 DEF_GEMM_SIMT(i64, int64_t)

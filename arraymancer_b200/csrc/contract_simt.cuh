@@ -96,6 +96,16 @@ struct StridedEpilogue {   // gemm_ukernel_generic.nim:96-125 semantics on a str
   int64_t rs, cs, M, N;
   T alpha, beta;
   bool vec_ok;             // cs == 1, 16-B aligned rows: whole vector in one transaction
+  // fused bias of the linear layer (nnp_linear.nim:28-29 `result +.= bias`, a separate pass in the reference): added
+  // AFTER the alpha / beta epilogue with its own rounding, exactly like the separate pass.  bias_n is indexed by the
+  // column of this kernel's product, bias_m by its row (the C^T = B^T A^T form swaps them); both may be null.
+  const T* bias_m = nullptr;
+  const T* bias_n = nullptr;
+  __device__ __forceinline__ T with_bias(T v, int64_t m, int64_t n) const {
+    if (bias_m) v = add_nocontract<T>(v, bias_m[m]);
+    if (bias_n) v = add_nocontract<T>(v, bias_n[n]);
+    return v;
+  }
   template <int V>
   __device__ __forceinline__ void store(int64_t m, int64_t n0, const T (&v)[V], int) const {
     if (m >= M || n0 >= N) return;
@@ -105,14 +115,14 @@ struct StridedEpilogue {   // gemm_ukernel_generic.nim:96-125 semantics on a str
       union { Vec q; T e[V]; } o, c;
       if (beta != T(0)) c.q = *reinterpret_cast<const Vec*>(row + n0);
 #pragma unroll
-      for (int j = 0; j < V; j++) o.e[j] = epilogue_value<T>(alpha, v[j], beta, beta != T(0) ? c.e[j] : T(0));
+      for (int j = 0; j < V; j++) o.e[j] = with_bias(epilogue_value<T>(alpha, v[j], beta, beta != T(0) ? c.e[j] : T(0)), m, n0 + j);
       *reinterpret_cast<Vec*>(row + n0) = o.q;
     } else {
 #pragma unroll
       for (int j = 0; j < V; j++) {
         if (n0 + j < N) {
           T* pc = row + (n0 + j) * cs;
-          *pc = epilogue_value<T>(alpha, v[j], beta, beta != T(0) ? *pc : T(0));
+          *pc = with_bias(epilogue_value<T>(alpha, v[j], beta, beta != T(0) ? *pc : T(0)), m, n0 + j);
         }
       }
     }

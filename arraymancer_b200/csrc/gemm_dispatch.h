@@ -23,6 +23,7 @@ enum TuneKey : int {
   kTuneConvTcDebug,        // "convtc_debug": per-role wait-cycle counters of the tcgen05 conv kernels (default 0)
   kTuneConvDgradGather,    // "convtc_dgrad_gather": older gather-form tcgen05 dgrad kernel under AM_CONV_TC (default 0)
   kTuneSimtVecLoad,        // "simt_vec_load": 128-bit global loads along a unit-stride operand dimension in the SIMT GEMM (default 1)
+  kTuneDmmaTma,            // "dmma_tma": TMA-fed 16-warp DMMA kernel for unit-stride float64 operands (default 1; 0: register-staged kernel)
   kTuneCount
 };
 int tuning(int key);
@@ -31,7 +32,16 @@ extern std::atomic<int> g_conv_path;          // conv.cu: AM_CONV_AUTO / AM_CONV
 // gemm_simt.cu — strided SIMT GEMM, any layout
 template <class T>
 int gemm_simt(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA,
-              const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC);
+              const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC, const T* bias_col = nullptr);
+// gemm_skinny.cu — DRAM-bound products with min(M, N) <= 16; *done == false -> not handled, use the general kernels
+template <class T>
+int gemm_skinny(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA, const T* B,
+                int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC, bool* done);
+// am_api.cu — the dispatch behind am_gemm_strided_f32 / _f64, with the optional fused per-column bias of the linear layer
+int gemm_dispatch_f32(cudaStream_t st, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t rsA, int64_t csA,
+                      const float* B, int64_t rsB, int64_t csB, float beta, float* C, int64_t rsC, int64_t csC, const float* bias_col);
+int gemm_dispatch_f64(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t rsA, int64_t csA,
+                      const double* B, int64_t rsB, int64_t csB, double beta, double* C, int64_t rsC, int64_t csC, const double* bias_col);
 
 // one launch for `batch` independent products (operand b at X + b*bsX), blockIdx.z = b
 template <class T>
@@ -43,7 +53,7 @@ int gemm_simt_batched(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int6
 // cta_group: 1 or 2
 int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                 int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
-                int64_t rsC, int64_t csC, const void* prepackedB = nullptr);
+                int64_t rsC, int64_t csC, const void* prepackedB = nullptr, const float* bias_col = nullptr);
 bool gemm_f32_tc_available();
 // pre-packed operands (two tf32 planes, K-major): pack once, multiply many
 int pack_f32(cudaStream_t st, int64_t R, int64_t K, const float* X, int64_t r_stride, int64_t k_stride, void** handle);
@@ -61,7 +71,7 @@ int gemm_packed_f32(cudaStream_t st, float alpha, const void* hA, const void* hB
 // gemm_f64_dmma.cu — FP64 tensor-pipe GEMM (mma.sync m8n8k4 f64), any strides
 int gemm_f64_dmma(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t rsA,
                   int64_t csA, const double* B, int64_t rsB, int64_t csB, double beta, double* C, int64_t rsC,
-                  int64_t csC);
+                  int64_t csC, const double* bias_col = nullptr);
 
 // conv.cu
 template <class T>

@@ -169,6 +169,10 @@ struct TcArgs {
   int npeers;
   int self;                // which peer[] entry is this GPU's own copy
   float* peer[8];
+  // fused bias of the linear layer (added after the alpha / beta epilogue, separately rounded like the reference's
+  // `result +.= bias` pass, nnp_linear.nim:28-29): indexed by the TMEM lane (row m of this kernel) or by its column
+  const float* bias_lane;
+  const float* bias_col;
 };
 
 // tile index -> (tm, tn): groups of |group| tiles of one dimension, that dimension fastest inside a group, so that
@@ -415,13 +419,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       } else if (m < p.M) {
         float* crow = p.C + m * p.rsC;
         const float alpha = p.alpha, beta = p.beta;
+        const float bl = p.bias_lane ? p.bias_lane[m] : 0.f;
 #pragma unroll
         for (int i = 0; i < 128; i++) {
           const int64_t n = col0 + half * 128 + i;
           if (n < p.N) {
             float* pc = crow + n * p.csC;
             const float cold = (beta != 0.f) ? *pc : 0.f;
-            *pc = epilogue_value<float>(alpha, acc[i], beta, cold);
+            float v = epilogue_value<float>(alpha, acc[i], beta, cold);
+            if (p.bias_lane) v = __fadd_rn(v, bl);
+            if (p.bias_col) v = __fadd_rn(v, p.bias_col[n]);
+            *pc = v;
           }
         }
       }
@@ -489,6 +497,21 @@ int make_tmap_f32_nd(CUtensorMap* tm, const float* base, int rank, const uint64_
   return AM_OK;
 }
 
+// Dense 2-D float64 tensor map (inner dimension first) for the TMA-fed DMMA kernel; zero fill outside the tensor.
+int make_tmap_f64_2d(CUtensorMap* tm, const double* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
+  if (!gemm_f32_tc_available()) { set_last_error("TMA needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {outer_stride_bytes};
+  cuuint32_t bx[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1u, 1u};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (f64) failed (%d)", (int)r); return AM_ERR_CUDA; }
+  return AM_OK;
+}
+
 template <int CG>
 static int launch_tc(cudaStream_t st, const CUtensorMap* tms, const TcArgs& args) {
   using Cfg = TcCfg<CG>;
@@ -545,7 +568,7 @@ static int pack_into(cudaStream_t st, const float* X, int64_t R, int64_t K, int6
 // P rows -> TMEM lanes (C's unit-stride dimension), Q rows -> TMEM columns.
 static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const PackedF32& Q, float alpha,
                       float beta, float* C, int64_t strideP, int64_t strideQ, int npeers = 0, float* const* peers = nullptr,
-                      int self = 0) {
+                      int self = 0, const float* bias_p = nullptr, const float* bias_q = nullptr) {
   if (P.Kpad != Q.Kpad || P.K != Q.K) { set_last_error("gemm_f32_tc: packed operands disagree on K"); return AM_ERR_INVALID; }
   const int flush_env = tuning(kTuneTcFlushKb) > 0 ? tuning(kTuneTcFlushKb) : 2;
   const int bk = 32;
@@ -558,7 +581,7 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
   const int group_env = tuning(kTuneTcGroup) != 0 ? tuning(kTuneTcGroup) : 8;   // > 0: groups of M-tiles (M fastest), < 0: groups of N-tiles
   args.M = P.R; args.N = Q.R; args.kblocks = (int)(P.Kpad / bk); args.flush_kb = flush_env; args.group = group_env;
   args.C = C; args.rsC = strideP; args.csC = strideQ; args.alpha = alpha; args.beta = beta;
-  args.npeers = npeers; args.self = self;
+  args.npeers = npeers; args.self = self; args.bias_lane = bias_p; args.bias_col = bias_q;
   for (int g = 0; g < 8; g++) args.peer[g] = (g < npeers) ? peers[g] : nullptr;
   // grid-barrier counter of the persistent schedule: one slot of a small ring, zeroed in stream order
   args.sync_counter = nullptr;
@@ -583,7 +606,7 @@ static int run_packed(cudaStream_t st, int cta_group, const PackedF32& P, const 
 // "b" role, i.e. rows = n) and is reused as is — only A is packed here (row chunks of one host-buffer product).
 int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                 int64_t rsA, int64_t csA, const float* B, int64_t rsB, int64_t csB, float beta, float* C,
-                int64_t rsC, int64_t csC, const void* prepackedB) {
+                int64_t rsC, int64_t csC, const void* prepackedB, const float* bias_col) {
   if (!gemm_f32_tc_available()) { set_last_error("tcgen05 path needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
   if (M >= (1ll << 31) - 1024 || N >= (1ll << 31) - 1024 || K >= (1ll << 31) - 64) { set_last_error("gemm_f32_tc: dimension too large"); return AM_ERR_INVALID; }
   // Operands in (panel-row stride, k stride) form: A panel rows = m, B panel rows = n.
@@ -605,8 +628,9 @@ int gemm_f32_tc(cudaStream_t st, int cta_group, int64_t M, int64_t N, int64_t K,
   }
   // The epilogue's lanes run along the P rows (TMEM lanes): make that C's unit-stride dimension.
   // Column-major C (rs == 1, the CudaTensor default): P = A.  Row-major C: C^T = B^T A^T, P = B.
-  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, cta_group, pa, pb, alpha, beta, C, rsC, csC);
-  return run_packed(st, cta_group, pb, pa, alpha, beta, C, csC, rsC);
+  // (bias is per column n of C: the Q index when P = A, the lane index when P = B)
+  if (iabs64(rsC) <= iabs64(csC)) return run_packed(st, cta_group, pa, pb, alpha, beta, C, rsC, csC, 0, nullptr, 0, nullptr, bias_col);
+  return run_packed(st, cta_group, pb, pa, alpha, beta, C, csC, rsC, 0, nullptr, 0, bias_col, nullptr);
 }
 
 // ---- pre-packed operands (laser's gemm_prepacked.nim:276-293 on the device): pack once, multiply many

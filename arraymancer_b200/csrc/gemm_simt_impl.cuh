@@ -61,13 +61,13 @@ static int stage_mode(const T* p, int64_t mn_stride, int64_t k_stride, int64_t b
 template <class T, class Cfg, bool Batched>
 static int launch_cfg(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t a_mn,
                       int64_t a_k, int64_t bsA, const T* B, int64_t b_mn, int64_t b_k, int64_t bsB, T beta, T* C,
-                      int64_t rsC, int64_t csC, int64_t bsC) {
+                      int64_t rsC, int64_t csC, int64_t bsC, const T* bias_m = nullptr, const T* bias_n = nullptr) {
   using LA = StridedLoader<T>;
   using Epi = StridedEpilogue<T>;
   LA la{A, a_mn, a_k, M, K};
   LA lb{B, b_mn, b_k, N, K};
   const bool vec_ok = (csC == 1) && (rsC % Cfg::V == 0) && (bsC % Cfg::V == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-  Epi epi{C, rsC, csC, M, N, alpha, beta, vec_ok};
+  Epi epi{C, rsC, csC, M, N, alpha, beta, vec_ok, bias_m, bias_n};
   const int a_kfast = iabs64(a_k) <= iabs64(a_mn);
   const int b_kfast = iabs64(b_k) <= iabs64(b_mn);
   dim3 grid((unsigned)ceil_div(N, Cfg::BN), (unsigned)ceil_div(M, Cfg::BM), (unsigned)(Batched ? batch : 1));
@@ -76,7 +76,7 @@ static int launch_cfg(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int6
     for (int64_t r = 0; r < M; r += band) {
       const int64_t mb = (M - r < band) ? M - r : band;
       int rc = launch_cfg<T, Cfg, Batched>(st, batch, mb, N, K, alpha, A + r * a_mn, a_mn, a_k, bsA, B, b_mn, b_k, bsB, beta,
-                                           C + r * rsC, rsC, csC, bsC);
+                                           C + r * rsC, rsC, csC, bsC, bias_m ? bias_m + r : nullptr, bias_n);
       if (rc) return rc;
     }
     return AM_OK;
@@ -112,9 +112,10 @@ static int launch_cfg(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int6
 template <class T>
 static int gemm_simt_any(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
                          int64_t csA, int64_t bsA, const T* B, int64_t rsB, int64_t csB, int64_t bsB, T beta, T* C,
-                         int64_t rsC, int64_t csC, int64_t bsC) {
+                         int64_t rsC, int64_t csC, int64_t bsC, const T* bias_col = nullptr) {
   // Operand views in (mn_stride, k_stride) form.  A: mn = row, B: mn = column.
   int64_t a_mn = rsA, a_k = csA, b_mn = csB, b_k = rsB;
+  const T *bias_m = nullptr, *bias_n = bias_col;     // bias is per column of C; the transposed form below makes it per row
   // Column-major-ish C (the CudaTensor default, data_structure.nim:44-58): compute
   // C^T = B^T A^T so the fast dimension of C maps onto the lanes' vector dimension.
   if (iabs64(rsC) < iabs64(csC)) {
@@ -125,6 +126,7 @@ static int gemm_simt_any(cudaStream_t st, int64_t batch, int64_t M, int64_t N, i
     t = M; M = N; N = t;
     t = rsC; rsC = csC; csC = t;
     t = bsA; bsA = bsB; bsB = t;
+    bias_m = bias_col; bias_n = nullptr;
   }
   // pick the tile: full 128x128 tiles when they fill the chip, 64x64 otherwise
   const int sms = sm_count();
@@ -151,15 +153,15 @@ static int gemm_simt_any(cudaStream_t st, int64_t batch, int64_t M, int64_t N, i
   }
   if (big)
     return launch_cfg<T, typename GemmCfgs<T>::Big, false>(st, 1, M, N, K, alpha, A, a_mn, a_k, 0, B, b_mn, b_k, 0, beta, C,
-                                                           rsC, csC, 0);
+                                                           rsC, csC, 0, bias_m, bias_n);
   return launch_cfg<T, typename GemmCfgs<T>::Small, false>(st, 1, M, N, K, alpha, A, a_mn, a_k, 0, B, b_mn, b_k, 0, beta, C,
-                                                           rsC, csC, 0);
+                                                           rsC, csC, 0, bias_m, bias_n);
 }
 
 template <class T>
 int gemm_simt(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA,
-              const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC) {
-  return gemm_simt_any<T>(st, 0, M, N, K, alpha, A, rsA, csA, 0, B, rsB, csB, 0, beta, C, rsC, csC, 0);
+              const T* B, int64_t rsB, int64_t csB, T beta, T* C, int64_t rsC, int64_t csC, const T* bias_col) {
+  return gemm_simt_any<T>(st, 0, M, N, K, alpha, A, rsA, csA, 0, B, rsB, csB, 0, beta, C, rsC, csC, 0, bias_col);
 }
 template <class T>
 int gemm_simt_batched(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA,
@@ -171,7 +173,7 @@ int gemm_simt_batched(cudaStream_t st, int64_t batch, int64_t M, int64_t N, int6
 
 #define AM_INST_SIMT(T)                                                                                                  \
   template int gemm_simt<T>(cudaStream_t, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, const T*, int64_t,   \
-                            int64_t, T, T*, int64_t, int64_t);                                                           \
+                            int64_t, T, T*, int64_t, int64_t, const T*);                                                 \
   template int gemm_simt_batched<T>(cudaStream_t, int64_t, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t,     \
                                     int64_t, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, int64_t, int64_t);
 

@@ -255,7 +255,7 @@ int gemm_skinny(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const
   a.part = nullptr;
   if (splits > 1) {
     void* p = nullptr;
-    int rc = workspace(kWsMisc + 8, (size_t)(splits * SP * a.Gd) * sizeof(T), &p);      // slot kWsSkinny
+    int rc = workspace(kWsSkinny, (size_t)(splits * SP * a.Gd) * sizeof(T), &p);
     if (rc) return rc;
     a.part = (T*)p;
   }

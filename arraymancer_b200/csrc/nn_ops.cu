@@ -264,9 +264,15 @@ template <class T>
 int linear_forward(cudaStream_t st, int64_t batch, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y) {
   if (batch < 0 || in < 0 || out < 0) { set_last_error("linear_forward: negative extent"); return AM_ERR_INVALID; }
   if (batch == 0 || out == 0) return AM_OK;
-  int rc = gemm_strided<T>(st, batch, out, in, T(1), x, in, 1, w, 1, in, T(0), y, out, 1);      // W^T as a view (rs = 1, cs = in)
-  if (rc) return rc;
-  if (in == 0) AM_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)(batch * out) * sizeof(T), st));       // empty product (K = 0 leaves C untouched)
+  if (in > 0) {
+    // y = x * W^T (W^T as a view: rs = 1, cs = in) with `+ bias` fused into the GEMM epilogue (the
+    // reference adds it in a second pass, nnp_linear.nim:28-29): same value, rounded like the separate pass
+    if constexpr (std::is_same<T, float>::value)
+      return gemm_dispatch_f32(st, batch, out, in, 1.f, x, in, 1, w, 1, in, 0.f, y, out, 1, bias);
+    else
+      return gemm_dispatch_f64(st, batch, out, in, 1.0, x, in, 1, w, 1, in, 0.0, y, out, 1, bias);
+  }
+  AM_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)(batch * out) * sizeof(T), st));       // empty product: y = bias
   if (bias) {
     add_bias_rows_kernel<T><<<grid_for(batch * out, 256), 256, 0, st>>>(y, bias, batch, out);
     g_launch_count++;

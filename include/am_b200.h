@@ -51,6 +51,7 @@ AM_API int am_shutdown(void);
  *   "host_rowchunks" (0)  am_host_gemm_strided_f32 uses row chunks only (no K pipeline)
  *   "convtc_groups" (0 = kernel default), "convtc_debug" (0), "convtc_dgrad_gather" (0): tcgen05 conv kernels
  *   "simt_vec_load" (1)  128-bit global accesses along a unit-stride operand dimension in the SIMT GEMM
+ *   "dmma_tma" (1)     TMA-fed 16-warp DMMA kernel for unit-stride float64 operands (0: register-staged 8-warp kernel)
  * Unknown names return AM_ERR_INVALID. */
 AM_API int am_set_tuning(const char* name, int value);
 AM_API int am_get_tuning(const char* name, int* value);

@@ -363,8 +363,9 @@ __global__ void __launch_bounds__(256) c1_reduce_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------ host side
 static bool c1_shape_ok(const am_conv2d_desc& d, int64_t Wo) {
-  // TMA staging: global row strides must be multiples of 16 bytes
-  return d.C == 1 && d.strideH == 1 && d.strideW == 1 && d.dilH == 1 && d.dilW == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) &&
+  // TMA staging: global row strides must be multiples of 16 bytes, and so must the byte offset of the box start along the
+  // innermost dimension (-padW elements): padW % 4 == 0 (a misaligned start coordinate is an illegal instruction)
+  return d.padW % 4 == 0 && d.C == 1 && d.strideH == 1 && d.strideW == 1 && d.dilH == 1 && d.dilW == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) &&
          d.Cout >= 1 && d.Cout <= 64 && d.H <= 64 && d.W <= 64 && d.padH < d.kH && d.padW < d.kW && d.W % 4 == 0 && Wo % 4 == 0 &&
          d.N < (1ll << 31);
 }

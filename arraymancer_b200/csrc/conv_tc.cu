@@ -29,6 +29,24 @@
 
 namespace am {
 
+// Per-role wait-cycle counters (tuning knob "convtc_debug") cost two clock reads around every mbarrier wait — in the
+// single-thread MMA issue loop that is ~150 cycles per k block.  They are compiled out unless AM_CONVTC_PROFILE is set:
+// pclk() is then a constant and the counters fold away.
+#ifndef AM_CONVTC_PROFILE
+#define AM_CONVTC_PROFILE 0
+#endif
+#ifndef AM_PCLK_DEFINED
+#define AM_PCLK_DEFINED
+__device__ __forceinline__ long long pclk() {
+#if AM_CONVTC_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
+#endif
+
+
 struct ConvTcArgs {
   const float* x;       // [N][C][H][W]        (grad_output for dgrad)
   const float* bias;    // [CO] or null
@@ -87,7 +105,7 @@ constexpr int kCtAStages = 6;             // im2col operand stages in tensor mem
 constexpr int kCtAccCols = 128;           // two accumulator buffers of up to 64 columns
 constexpr int kCtMaxBStages = 8;
 
-#define CT_TWAIT(counter, bar, ph) do { const long long t0_ = clock64(); ptx::mbar_wait(bar, ph); counter += clock64() - t0_; } while (0)
+#define CT_TWAIT(counter, bar, ph) do { const long long t0_ = pclk(); ptx::mbar_wait(bar, ph); counter += pclk() - t0_; } while (0)
 
 template <bool CHECK>
 __global__ void __launch_bounds__(768, 1)
@@ -164,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       if (ptx::elect_one()) {
         uint32_t it = 0;
         long long w_eb = 0;
-        const long long tstart = clock64();
+        const long long tstart = pclk();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
           for (int kb = 0; kb < nkb; kb++, it++) {
             const int s = it % SB;
@@ -175,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
             ptx::tma_load_2d(sb + OFF_BLO, &tmWlo, full_b(s), kb * 32, 0);
           }
         }
-        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - tstart; a.dbg[1] = w_eb; }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_eb; }
       }
     } else if (warp == 1) {
       // ===================== UMMA issuer: A from tensor memory, B from shared memory =====================
@@ -184,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
         const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
         uint32_t it = 0, chain = 0;
         long long w_te = 0, w_fa = 0, w_fb = 0;
-        const long long tstart = clock64();
+        const long long tstart = pclk();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
           int kb = 0;
           for (int c = 0; c < chains_per_tile; c++, chain++) {
@@ -215,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
             ptx::umma_commit<1>(tfull_bar(buf));
           }
         }
-        if (a.dbg && blockIdx.x == 0) { a.dbg[2] = clock64() - tstart; a.dbg[3] = w_te; a.dbg[4] = w_fa; a.dbg[5] = w_fb; }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[2] = pclk() - tstart; a.dbg[3] = w_te; a.dbg[4] = w_fa; a.dbg[5] = w_fb; }
       }
     } else if (warp == 3) {
       // ===================== raw-image producer: whole images of the tile, one contiguous bulk copy =====================
@@ -244,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kCtAccCols;
     uint32_t ti = 0;
     long long w_rf = 0, w_ea = 0, w_st = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ti++) {
       const int64_t p0 = (int64_t)tile * 128;
       const int64_t p = p0 + r;
@@ -293,13 +311,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
           ptx::tmem_st_32x16(ta + 16u * half, hi);
           ptx::tmem_st_32x16(ta + 32u + 16u * half, lo);
         }
-        { const long long t0_ = clock64(); ptx::tmem_st_wait(); w_st += clock64() - t0_; }
+        { const long long t0_ = pclk(); ptx::tmem_st_wait(); w_st += pclk() - t0_; }
         ptx::tc_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a(sa)) : "memory");
       }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(raw_empty(b)) : "memory");   // done reading this tile's images
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[7] = clock64() - tstart; a.dbg[8] = w_rf; a.dbg[9] = w_ea; a.dbg[10] = w_st; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[7] = pclk() - tstart; a.dbg[8] = w_rf; a.dbg[9] = w_ea; a.dbg[10] = w_st; }
   } else if (warp < acc_warp0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else {
@@ -309,7 +327,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
     const int r = q * 32 + (int)lane;                      // TMEM lane = pixel row of the tile
     uint32_t chain = 0;
     long long w_tf = 0, w_ep = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       float acc[64];
 #pragma unroll
@@ -338,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
       }
       // epilogue: out[n][co][ho][wo] = acc[co] + bias[co]; consecutive lanes = consecutive pixels
-      const long long te_ = clock64();
+      const long long te_ = pclk();
       const int64_t p = (int64_t)tile * 128 + r;
       if (p < a.P) {
         const int64_t n = p / HW, rem = p - n * HW;
@@ -359,9 +377,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
           }
         }
       }
-      w_ep += clock64() - te_;
+      w_ep += pclk() - te_;
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[11] = clock64() - tstart; a.dbg[12] = w_tf; a.dbg[13] = w_ep; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[11] = pclk() - tstart; a.dbg[12] = w_tf; a.dbg[13] = w_ep; }
   }
 
   __syncwarp();

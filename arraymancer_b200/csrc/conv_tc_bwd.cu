@@ -30,6 +30,24 @@
 
 namespace am {
 
+// Per-role wait-cycle counters (tuning knob "convtc_debug") cost two clock reads around every mbarrier wait — in the
+// single-thread MMA issue loop that is ~150 cycles per k block.  They are compiled out unless AM_CONVTC_PROFILE is set:
+// pclk() is then a constant and the counters fold away.
+#ifndef AM_CONVTC_PROFILE
+#define AM_CONVTC_PROFILE 0
+#endif
+#ifndef AM_PCLK_DEFINED
+#define AM_PCLK_DEFINED
+__device__ __forceinline__ long long pclk() {
+#if AM_CONVTC_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
+#endif
+
+
 struct DgradTcArgs {
   const float* gout;    // [N][CO][HO][WO]
   float* gin;           // [N][C][H][W]
@@ -141,13 +159,13 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
       ptx::mbar_wait(b_full, 0);
       uint32_t it = 0;
       long long w_de = 0, w_af = 0;
-      const long long tstart = clock64();
+      const long long tstart = pclk();
       for (int64_t g = g0; g < a.ngroups; g += gstep) {
         for (int t = 0; t < a.tpg; t++, it++) {
           const int s = it & 1;
           const uint32_t ph = (it >> 1) & 1u;
-          { const long long t0_ = clock64(); ptx::mbar_wait(d_empty(s), ph ^ 1u); w_de += clock64() - t0_; }
-          { const long long t0_ = clock64(); ptx::mbar_wait(a_full(s), ph); w_af += clock64() - t0_; }
+          { const long long t0_ = pclk(); ptx::mbar_wait(d_empty(s), ph ^ 1u); w_de += pclk() - t0_; }
+          { const long long t0_ = pclk(); ptx::mbar_wait(a_full(s), ph); w_af += pclk() - t0_; }
           ptx::tc_fence_after();
           const uint32_t d = tmem_base + 128u * (uint32_t)s;
           const uint32_t a_hi0 = tmem_a0 + (uint32_t)s * 2u * (uint32_t)a.Kpad, a_lo0 = a_hi0 + (uint32_t)a.Kpad;
@@ -162,7 +180,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
           ptx::umma_commit<1>(d_full(s));
         }
       }
-      if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - tstart; a.dbg[1] = w_de; a.dbg[2] = w_af; }
+      if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_de; a.dbg[2] = w_af; }
     }
   }
   } else if (warp < 8) {
@@ -172,7 +190,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
     const uint32_t t_lane = tmem_a0 + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t it = 0;
     long long w_ae = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int64_t g = g0; g < a.ngroups; g += gstep) {
       const int64_t n0 = g * a.ipg;
       const int imgs = (a.N - n0 < a.ipg) ? (int)(a.N - n0) : a.ipg;
@@ -188,7 +206,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         float v[64];
 #pragma unroll
         for (int j = 0; j < 64; j++) v[j] = (ok && j < a.CO) ? __ldg(src + (int64_t)j * HWo) : 0.f;
-        { const long long t0_ = clock64(); ptx::mbar_wait(a_empty(s), ((it >> 1) & 1u) ^ 1u); w_ae += clock64() - t0_; }
+        { const long long t0_ = pclk(); ptx::mbar_wait(a_empty(s), ((it >> 1) & 1u) ^ 1u); w_ae += pclk() - t0_; }
         ptx::tc_fence_after();
         const uint32_t ta = t_lane + (uint32_t)s * 2u * (uint32_t)a.Kpad;
 #pragma unroll
@@ -206,7 +224,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(s)) : "memory");
       }
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[3] = clock64() - tstart; a.dbg[4] = w_ae; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[3] = pclk() - tstart; a.dbg[4] = w_ae; }
   } else {
     // ===================== col2im warps (16 warps = 512 threads) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -249,7 +267,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
     }
     uint32_t it = 0;
     long long w_df = 0, w_p1 = 0, w_p2 = 0, w_fl = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int64_t g = g0; g < a.ngroups; g += gstep) {
       const int64_t n0 = g * a.ipg;
       const int imgs = (a.N - n0 < a.ipg) ? (int)(a.N - n0) : a.ipg;
@@ -259,8 +277,8 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         const int s = it & 1;
         const int q_lo = t * 128, q_hi = (q_lo + 128 < npix) ? q_lo + 128 : npix;      // group pixels this tile holds
         const bool whole = (q_lo == 0 && q_hi == npix);         // the tile holds every pixel of the group: no range test
-        { const long long t0_ = clock64(); ptx::mbar_wait(d_full(s), (it >> 1) & 1u); w_df += clock64() - t0_; }
-        const long long tp1 = clock64();
+        { const long long t0_ = pclk(); ptx::mbar_wait(d_full(s), (it >> 1) & 1u); w_df += pclk() - t0_; }
+        const long long tp1 = pclk();
         ptx::tc_fence_after();
         const uint32_t td = tmem_base + ((uint32_t)(wq * 32) << 16) + 128u * (uint32_t)s;
         // phase 1: D -> col_s[column][pixel] (lanes = consecutive pixels: conflict-free)
@@ -286,7 +304,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(d_empty(s)) : "memory");   // accumulator free again
         bar_sync_named(1, 512);
-        const long long tp2 = clock64();
+        const long long tp2 = pclk();
         w_p1 += tp2 - tp1;
         // phase 2: the input pixels this tile can touch (a row range when an image spans several tiles) x the chunk's
         // channels are dealt out to the 512 threads; each sums the taps that land on its pixel in a fixed order
@@ -400,9 +418,9 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
           }
         }
         bar_sync_named(1, 512);                                 // col_s may be overwritten by the next tile; gin_s complete
-        w_p2 += clock64() - tp2;
+        w_p2 += pclk() - tp2;
       }
-      const long long tfl = clock64();
+      const long long tfl = pclk();
       // flush the finished images (coalesced), leaving zeros behind for the next group; the first barrier of the next
       // tile orders these accesses before its accumulation phase
       const int nflush = pre ? 0 : cpc_here * nout;
@@ -414,9 +432,9 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
         *ga = 0.f;
         a.gin[((n0 + il) * a.C + ci0 + cl) * (int64_t)HWi + rem] = x;
       }
-      w_fl += clock64() - tfl;
+      w_fl += pclk() - tfl;
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 256) { a.dbg[5] = clock64() - tstart; a.dbg[6] = w_df; a.dbg[7] = w_p1; a.dbg[8] = w_p2; a.dbg[9] = w_fl; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 256) { a.dbg[5] = pclk() - tstart; a.dbg[6] = w_df; a.dbg[7] = w_p1; a.dbg[8] = w_p2; a.dbg[9] = w_fl; }
   }
 
   __syncwarp();
@@ -552,7 +570,7 @@ struct WgradTcArgs {
 };
 
 constexpr int kWgAStages = 6;
-#define WG_TWAIT(counter, bar, ph) do { const long long t0_ = clock64(); ptx::mbar_wait(bar, ph); counter += clock64() - t0_; } while (0)
+#define WG_TWAIT(counter, bar, ph) do { const long long t0_ = pclk(); ptx::mbar_wait(bar, ph); counter += pclk() - t0_; } while (0)
 
 
 __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs a) {
@@ -632,7 +650,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
         const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
         uint32_t chain = 0;
         long long w_te = 0, w_fa = 0, w_fb = 0;
-        const long long tstart = clock64();
+        const long long tstart = pclk();
         for (int64_t it = 0; it < T; it++) {
           const int in_chain = (int)(it % a.flush_st);
           const int buf = chain & 1;
@@ -658,7 +676,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
           ptx::umma_commit<1>(empty_b(sbi));
           if (in_chain == a.flush_st - 1 || it == T - 1) { ptx::umma_commit<1>(tfull_bar(buf)); chain++; }
         }
-        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - tstart; a.dbg[1] = w_te; a.dbg[2] = w_fa; a.dbg[3] = w_fb; }
+        if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_te; a.dbg[2] = w_fa; a.dbg[3] = w_fb; }
       }
     }
   } else if (warp < 4 + 4 * G) {
@@ -677,7 +695,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       kind = 2;
     }
     long long w_rf = 0, w_ea = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int64_t i = 0; i < nimg; i++) {
       const int b = (int)(i & 1);
       WG_TWAIT(w_rf, raw_full(b), (uint32_t)((i >> 1) & 1));      // every group waits for every image (keeps the phases of raw_empty in step)
@@ -730,7 +748,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(raw_empty(b)) : "memory");
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[4] = clock64() - tstart; a.dbg[5] = w_rf; a.dbg[6] = w_ea; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[4] = pclk() - tstart; a.dbg[5] = w_rf; a.dbg[6] = w_ea; }
   } else if (warp < 16) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // unused gather slots
   } else if (warp < 20) {
@@ -770,7 +788,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     float4 cur[4], nxt[4];
     if (T > 0) fetch(0, cur);
     long long w_eb = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int64_t it = 0; it < T; it++) {
       if (it + 1 < T) fetch(it + 1, nxt);
       const int sbi = (int)(it % SB);
@@ -798,7 +816,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
 #pragma unroll
       for (int v4 = 0; v4 < 4; v4++) cur[v4] = nxt[v4];
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[7] = clock64() - tstart; a.dbg[8] = w_eb; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[7] = pclk() - tstart; a.dbg[8] = w_eb; }
   } else {
     // ===================== accumulate warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
@@ -809,7 +827,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     for (int i = 0; i < 64; i++) acc[i] = 0.f;
     const int64_t nchains = (T + a.flush_st - 1) / a.flush_st;
     long long w_tf = 0;
-    const long long tstart = clock64();
+    const long long tstart = pclk();
     for (int64_t c = 0; c < nchains; c++) {
       const int buf = (int)(c & 1);
       WG_TWAIT(w_tf, tfull_bar(buf), (uint32_t)((c >> 1) & 1));
@@ -833,7 +851,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[9] = clock64() - tstart; a.dbg[10] = w_tf; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[9] = pclk() - tstart; a.dbg[10] = w_tf; }
     const int R = R0 + r;
     if (R < a.Nv) {
       float* dst = a.part + (int64_t)slice * a.CO * a.Nv + R;

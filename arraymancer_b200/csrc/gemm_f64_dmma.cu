@@ -132,14 +132,15 @@ contract_dmma_kernel(const LA la, const LB lb, const Epi epi, int64_t K, int a_k
 
 // ------------------------------------------------------------------ TMA-fed variant (unit-stride operands)
 // Operand tiles come in by cp.async.bulk.tensor (2-D boxes, zero fill outside the matrix = free edge handling) through a
-// 4-stage full / empty mbarrier ring: no staging instructions, no __syncthreads in the mainloop.  A box is laid out the way
+// 5-stage full / empty mbarrier ring: no staging instructions, no __syncthreads in the mainloop.  A box is laid out the way
 // the operand is stored: k-contiguous operands land as [128 rows][BK], mn-contiguous ones as [BK][128]; the DMMA fragment
 // loads index either (template flags).  The dense boxes cost 2-way bank conflicts on the 64-bit fragment loads, which is
-// irrelevant next to a DMMA issue interval of 16 cycles per scheduler.  16 warps x (32x32) warp tiles: four warps per
-// scheduler keep the FP64 tensor pipe busy while others wait for a stage (the 8-warp register-staged kernel above ran
+// irrelevant next to a DMMA issue interval of 16 cycles per scheduler.  Thread 0 is the producer (prologue of STAGES-1
+// tiles, then one refill per loop trip); 16 warps x (32x32) warp tiles consume: four per scheduler keep the FP64 tensor
+// pipe busy while others wait for a stage (the 8-warp register-staged kernel above ran
 // two per scheduler and two barriers per 8-deep tile: 0.79 of the DMMA peak).
 struct DmmaTmaCfg {
-  static constexpr int BM = 128, BN = 128, BK = 16, NT = 512, STAGES = 4;
+  static constexpr int BM = 128, BN = 128, BK = 16, NT = 512, STAGES = 5;
   static constexpr int TILE_BYTES = 128 * BK * 8;                  // one operand tile
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;               // 32 KB
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + 64;
@@ -186,12 +187,20 @@ contract_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   for (int t = 0; t < ntiles; t++) {
     const int s = t % S;
-    if (tid == 0 && t + S - 1 < ntiles) {
-      const int tn = t + S - 1, sn = tn % S;       // stage sn held tile t-1: all warps must have left it
-      if (tn >= S) ptx::mbar_wait(empty_bar(sn), (uint32_t)((tn / S - 1) & 1));
+    ptx::mbar_wait(full_bar(s), (uint32_t)((t / S) & 1));
+    // DELAYED release: the stage of tile t-1 is handed back only now, one loop trip after its last fragment load.  All
+    // DMMAs of tile t-1 were issued before this point (in-order issue, the arrive cannot be hoisted across the loop
+    // branch), and a DMMA issues only once its operands have arrived — so every shared-memory read of that stage has
+    // completed.  (Releasing at the end of the same trip let ptxas place the arrive right behind the last LDS, ahead
+    // of the DMMAs that consume it: the TMA refill could then overtake reads still in flight — observed as run-to-run
+    // differences at K >= 4096.)
+    if (t >= 1 && lane == 0) ptx::mbar_arrive(empty_bar((t - 1) % S));
+    if (tid == 0 && t >= 1 && t + S - 2 < ntiles) {
+      // tile t+S-2 goes into the stage tile t-2 occupied, released by every warp at the start of its trip t-1
+      const int tn = t + S - 2;
+      ptx::mbar_wait(empty_bar(tn % S), (uint32_t)((tn / S - 1) & 1));
       issue(tn);
     }
-    ptx::mbar_wait(full_bar(s), (uint32_t)((t / S) & 1));
     const double* As = sm + (size_t)s * (Cfg::STAGE_BYTES / 8);
     const double* Bs = As + Cfg::TILE_BYTES / 8;
 #pragma unroll
@@ -212,8 +221,6 @@ contract_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(empty_bar(s));
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) {

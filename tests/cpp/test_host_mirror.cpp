@@ -127,6 +127,80 @@ static void nn_known_answers() {
   EXPECT(std::fabs(sum) < 1e-6 && gl[3] < 0 && gl[0] > 0);      // softmax - onehot sums to zero
 }
 
+// Round-2 boundary entries straight through the C ABI: batched GEMM (cublas.nim:172-208), strided conv
+// (backend/cudnn.nim:59-75 strides), single-process multi-GPU (am_mg_*; device 0 listed twice on a one-GPU box).
+template <class T>
+static T* dev_copy(const std::vector<T>& h) {
+  T* d = nullptr;
+  cudaCheck(cudaMalloc(&d, h.size() * sizeof(T)));
+  cudaCheck(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+template <class T>
+static std::vector<T> host_copy(const T* d, size_t n) {
+  std::vector<T> h(n);
+  cudaCheck(cudaDeviceSynchronize());
+  cudaCheck(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+static void boundary_round2() {
+  // ---- batched: 3 products [2x3]*[3x2], B shared (batch stride 0); expected from gemm.nim:369-392 scaled per batch
+  std::vector<int64_t> a;
+  for (int b = 0; b < 3; b++) for (int v : {1, 2, 3, 4, 5, 6}) a.push_back((int64_t)v * (b + 1));
+  int64_t* dA = dev_copy(a);
+  int64_t* dB = dev_copy(std::vector<int64_t>{7, 8, 9, 10, 11, 12});
+  int64_t* dC = dev_copy(std::vector<int64_t>(12, -1));
+  amCheck(am_gemm_strided_batched_i64(nullptr, 3, 2, 2, 3, 1, dA, 3, 1, 6, dB, 2, 1, 0, 0, dC, 2, 1, 4));
+  EXPECT((host_copy(dC, 12) == std::vector<int64_t>{58, 64, 139, 154, 116, 128, 278, 308, 174, 192, 417, 462}));
+  // ---- strided conv: test_nnp_convolution.nim:21-46 with the input stored TRANSPOSED (W-major) and passed by strides
+  const std::vector<int64_t> x = {1, 2, 0, 0, 5, 3, 0, 4, 0, 0, 0, 7, 9, 3, 0, 0};
+  std::vector<int64_t> xt(16);
+  for (int h = 0; h < 4; h++) for (int w = 0; w < 4; w++) xt[w * 4 + h] = x[h * 4 + w];
+  int64_t* dX = dev_copy(xt);
+  int64_t* dK = dev_copy(std::vector<int64_t>{1, 1, 1, 1, 1, 0, 1, 0, 0});
+  int64_t* dY = dev_copy(std::vector<int64_t>(16, -1));
+  am_conv2d_desc d{1, 1, 4, 4, 1, 3, 3, 1, 1, 1, 1, 1, 1};
+  const int64_t xs[4] = {16, 16, 1, 4};            // element (n, c, h, w) at h + 4*w
+  amCheck(am_conv2d_forward_strided_i64(nullptr, &d, dX, xs, dK, nullptr, nullptr, 1, dY, nullptr, AM_ACT_NONE));
+  EXPECT((host_copy(dY, 16) == std::vector<int64_t>{1, 8, 5, 0, 8, 11, 5, 4, 8, 17, 10, 11, 9, 12, 10, 7}));
+  // backward with grad_output = ones given through a stride-0 broadcast view (all four strides 0)
+  int64_t* dOne = dev_copy(std::vector<int64_t>{1});
+  int64_t* dGi = dev_copy(std::vector<int64_t>(16, -1));
+  int64_t* dGk = dev_copy(std::vector<int64_t>(9, -1));
+  const int64_t zs[4] = {0, 0, 0, 0};
+  amCheck(am_conv2d_backward_strided_i64(nullptr, &d, dX, xs, dK, nullptr, dOne, zs, dGi, nullptr, dGk, nullptr, nullptr, 1));
+  // grad_kernel[kh][kw] = sum of the input window shifted by (kh-1, kw-1); total input sum = 34
+  auto gk = host_copy(dGk, 9);
+  EXPECT(gk[4] == 34);
+  auto gi = host_copy(dGi, 16);
+  EXPECT(gi[5] == 6);                               // interior pixel: all 6 non-zero taps of the kernel reach it
+  // ---- single-process multi-GPU entries: two "ranks" on device 0
+  int devs[2] = {0, 0};
+  am_mg_ctx* ctx = nullptr;
+  amCheck(am_mg_init(2, devs, &ctx));
+  const int64_t M = 5, N = 4, K = 4;               // gemm.nim:420-451
+  const std::vector<int64_t> A5 = {5, 6, 5, 8, 8, 2, 8, 8, 0, 5, 4, 0, 4, 0, 5, 6, 4, 5, 0, 3};
+  const std::vector<int64_t> B4 = {5, 3, 6, 0, 5, 2, 3, 3, 8, 8, 2, 0, 7, 7, 0, 0};
+  int64_t r0[2], rn[2];
+  const int64_t* Al[2]; const int64_t* Bl[2]; int64_t* Cl[2];
+  for (int g = 0; g < 2; g++) {
+    amCheck(am_mg_rows(ctx, M, g, &r0[g], &rn[g]));
+    Al[g] = dev_copy(std::vector<int64_t>(A5.begin() + r0[g] * K, A5.begin() + (r0[g] + rn[g]) * K));
+    Bl[g] = dev_copy(B4);
+    Cl[g] = dev_copy(std::vector<int64_t>(M * N, -1));
+  }
+  EXPECT(rn[0] + rn[1] == M);
+  amCheck(am_mg_gemm_rowsharded_i64(ctx, M, N, K, 1, Al, K, Bl, N, Cl, N));
+  amCheck(am_mg_synchronize(ctx));
+  const std::vector<int64_t> want = {151, 123, 58, 18, 170, 148, 70, 6, 57, 42, 23, 15, 102, 94, 34, 0, 66, 43, 39, 15};
+  EXPECT(host_copy(Cl[0], 20) == want);
+  EXPECT(host_copy(Cl[1], 20) == want);
+  amCheck(am_mg_destroy(ctx));
+  for (void* p : {(void*)dA, (void*)dB, (void*)dC, (void*)dX, (void*)dK, (void*)dY, (void*)dOne, (void*)dGi, (void*)dGk,
+                  (void*)Al[0], (void*)Al[1], (void*)Bl[0], (void*)Bl[1], (void*)Cl[0], (void*)Cl[1]}) cudaFree(p);
+}
+
 int main() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { std::printf("SKIP: no GPU\n"); return 77; }
@@ -140,6 +214,7 @@ int main() {
   conv_known_answers<int64_t>();
   nn_known_answers<float>();
   nn_known_answers<double>();
+  boundary_round2();
   am_shutdown();
   std::printf("OK %d checks\n", checks);
   return 0;

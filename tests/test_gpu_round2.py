@@ -345,3 +345,38 @@ def test_mg_host_gemm_f32(am, oracle):
         ctx.host_gemm_f32(1.0, A, B, C)
         assert rel_fro(C.numpy(), oracle.matmul(a, b)) <= F32_TOL, devs
         ctx.close()
+
+
+def test_f64_dmma_tma_kernel_matches_register_staged_kernel_and_is_deterministic(am):
+    """The TMA-fed DMMA kernel (producer warp + 4-stage mbarrier ring) against the register-staged one on every
+    operand layout, edge tiles and a K tail; repeated runs must be bit-identical (a stage overwritten early would show
+    up as run-to-run differences at large K)."""
+    from arraymancer_b200 import _capi
+    am.set_f64_path(am.F64_DMMA)
+    try:
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        for (M, N, K) in [(2048, 2304, 8192), (300, 260, 1001 * 2), (130, 4100, 70)]:
+            Ar = torch.rand((M, K), device="cuda", dtype=torch.float64, generator=g) - 0.5
+            Br = torch.rand((K, N), device="cuda", dtype=torch.float64, generator=g) - 0.5
+            Ac = Ar.t().contiguous().t(); Bc = Br.t().contiguous().t()
+            for A in (Ar, Ac):
+                for B in (Br, Bc):
+                    for order in ("C", "F"):
+                        C0 = torch.empty((M, N), device="cuda", dtype=torch.float64)
+                        C1 = torch.empty((M, N), device="cuda", dtype=torch.float64)
+                        if order == "F":
+                            C0 = C0.t().contiguous().t(); C1 = C1.t().contiguous().t()
+                        _capi.set_tuning("dmma_tma", 0); am.gemm_strided(1, A, B, 0, C0)
+                        _capi.set_tuning("dmma_tma", 1); am.gemm_strided(1, A, B, 0, C1)
+                        assert rel_fro(C1.cpu().numpy(), C0.cpu().numpy()) <= 1e-14, (M, N, K, A.stride(), B.stride(), order)
+        M, N, K = 2048, 2048, 16384
+        A = torch.rand((M, K), device="cuda", dtype=torch.float64, generator=g) - 0.5
+        B = torch.rand((K, N), device="cuda", dtype=torch.float64, generator=g) - 0.5
+        C1 = torch.empty((M, N), device="cuda", dtype=torch.float64); C2 = torch.empty_like(C1)
+        am.gemm_strided(1, A, B, 0, C1)
+        for _ in range(6):
+            am.gemm_strided(1, A, B, 0, C2)
+            assert torch.equal(C1, C2)
+    finally:
+        _capi.set_tuning("dmma_tma", 1)
+        am.set_f64_path(am.F64_AUTO)

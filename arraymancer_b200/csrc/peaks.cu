@@ -48,6 +48,30 @@ __global__ void __launch_bounds__(256) simt_peak_kernel(T* out, int iters, T a0,
   if (s == (T)123457) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed FP32: fma.rn.f32x2 (SASS FFMA2) does two FMAs per lane and instruction on aligned 64-bit register pairs
+template <int CHAINS>
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, float a0, float b0) {
+  unsigned long long acc[CHAINS], bb[CHAINS], a;
+  {
+    const float ax = a0 + threadIdx.x * 1e-6f, ay = a0 - threadIdx.x * 1e-6f;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(ax), "f"(ay));
+  }
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) {
+    const float f = (float)i, g = b0 + i * 0.001f;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(f), "f"(-f));
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(bb[i]) : "f"(g), "f"(g + 0.0005f));
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(a), "l"(bb[i]));
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) { float x, y; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc[i])); s += x + y; }
+  if (s == 123457.f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // mma.sync m8n8k4 f64: 8x8x4 = 256 FMA per warp instruction
 template <int CHAINS>
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
@@ -185,6 +209,11 @@ int microbench(int which, double* tops) {
       const int iters = 1 << 14;
       rc = time_launch([&] { i64_narrow_peak_kernel<CH><<<blocks, threads>>>((int64_t*)scratch, iters, 3, 5); g_launch_count++; }, 3, &ms);
       ops = 2.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 13: {   // packed FFMA2: two FMAs per lane and instruction
+      const int iters = 1 << 15;
+      rc = time_launch([&] { ffma2_peak_kernel<CH><<<blocks, threads>>>((float*)scratch, iters, 1.0001f, 0.9999f); g_launch_count++; }, 3, &ms);
+      ops = 4.0 * CH * (double)iters * blocks * threads;
     } break;
     case 5:
     case 6:

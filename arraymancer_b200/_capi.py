@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarraymancer_b200.so")
+# AM_B200_LIB: developer override, e.g. the profiling build libarraymancer_b200_prof.so (make -C arraymancer_b200/csrc prof)
+LIB_PATH = os.environ.get("AM_B200_LIB") or os.path.join(_HERE, "libarraymancer_b200.so")
 
 AM_OK, AM_ERR_INVALID, AM_ERR_CUDA, AM_ERR_UNSUPPORTED, AM_ERR_NONCONTIGUOUS = range(5)
 F32_AUTO, F32_SIMT, F32_TC, F32_TC_1CTA = range(4)

@@ -55,6 +55,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// ---- packed FP32: two FMAs per lane and instruction (SASS FFMA2).  (d0, d1) += (a0, a1) * (b0, b1), each lane an IEEE
+// fma.rn exactly like fmaf.  ptxas folds a duplicated multiplier ({w, w}) into a scalar `.F32` operand and register
+// pairs taken in swapped order into a `.LO_HI` modifier, so only genuinely misaligned pairs cost a MOV.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// 64-bit register-pair forms: the caller keeps operand pairs (pack2) and accumulator pairs alive across loops, so that a
+// pair that is not naturally aligned (x[j], x[j+1] with odd j) is materialised ONCE and not per use.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// acc += {w, w} * b
+__device__ __forceinline__ void ffma2_s(uint64_t& acc, float w, uint64_t b) {
+  asm("{\n\t.reg .b64 ra;\n\tmov.b64 ra, {%1, %1};\n\tfma.rn.f32x2 %0, ra, %2, %0;\n\t}" : "+l"(acc) : "f"(w), "l"(b));
+}
+// acc += a * b
+__device__ __forceinline__ void ffma2_v(uint64_t& acc, uint64_t a, uint64_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 // ---- TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");

@@ -65,6 +65,7 @@ struct ConvTcArgs {
   uint32_t raw_bytes;   // bytes of one raw-image buffer (max images a tile touches * CHW * 4, rounded up)
   long long* dbg;       // optional: per-role wait-cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
   int relu;             // fused activation: y = max(0, conv + bias)
+  int skip;             // experiments (knob convtc_debug >> 1): bit 0 = gather warps skip their loads / stores to TMEM, bit 1 = no output stores
 };
 
 constexpr int kCtABytes = 128 * 128;      // one plane of the im2col tile: 128 pixels x 32 floats
@@ -180,17 +181,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
     if (warp == 0) {
       // ===================== TMA producer: weight tiles (own ring, runs ahead of the operand stages) =====================
       if (ptx::elect_one()) {
-        uint32_t it = 0;
+        int s = 0; uint32_t ph = 1u;                  // ring position and wait parity, advanced without divisions
         long long w_eb = 0;
         const long long tstart = pclk();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-          for (int kb = 0; kb < nkb; kb++, it++) {
-            const int s = it % SB;
-            CT_TWAIT(w_eb, empty_b(s), ((it / SB) & 1u) ^ 1u);
+          for (int kb = 0; kb < nkb; kb++) {
+            CT_TWAIT(w_eb, empty_b(s), ph);
             const uint32_t sb = stage_base(s);
             ptx::mbar_arrive_expect_tx(full_b(s), 2 * b_bytes);
             ptx::tma_load_2d(sb + OFF_BHI, &tmWhi, full_b(s), kb * 32, 0);
             ptx::tma_load_2d(sb + OFF_BLO, &tmWlo, full_b(s), kb * 32, 0);
+            if (++s == SB) { s = 0; ph ^= 1u; }
           }
         }
         if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_eb; }
@@ -200,7 +201,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       if (ptx::elect_one()) {
         const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
         const uint32_t idesc = ptx::umma_idesc_tf32(128, (uint32_t)a.NP);
-        uint32_t it = 0, chain = 0;
+        uint32_t chain = 0;
+        // ring positions / wait parities of the two operand rings advance by compare-and-wrap: the issuing thread runs
+        // nothing but a dozen uniform-register adds between two batches of MMAs (a division by the run-time ring depth
+        // plus the multiply-shift by 6 used to cost ~90 dependent instructions per k block: 66 cycles per MMA where the
+        // same issue pattern alone sustains 38, am_microbench 27/31)
+        int sa = 0, sbi = 0; uint32_t pa = 0u, pb = 0u;
+        uint32_t a_hi0 = tmem_base + (uint32_t)kCtAccCols;
+        uint64_t b_hi0 = ptx::umma_desc(dhi, stage_base(0) + OFF_BHI), b_lo0 = ptx::umma_desc(dhi, stage_base(0) + OFF_BLO);
+        const uint64_t b_hi_first = b_hi0, b_lo_first = b_lo0, b_step = (uint64_t)(stage_bytes >> 4);
         long long w_te = 0, w_fa = 0, w_fb = 0;
         const long long tstart = pclk();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -211,24 +220,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
             ptx::tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)buf * 64u;
             const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
-            for (bool first = true; kb < kb_end; kb++, it++) {
-              const int sa = it % kCtAStages, sbi = it % SB;
-              CT_TWAIT(w_fa, full_a(sa), (it / kCtAStages) & 1u);
-              CT_TWAIT(w_fb, full_b(sbi), (it / SB) & 1u);
+            for (uint32_t acc_on = 0u; kb < kb_end; kb++) {
+              CT_TWAIT(w_fa, full_a(sa), pa);
+              CT_TWAIT(w_fb, full_b(sbi), pb);
               ptx::tc_fence_after();
-              const uint32_t sb = stage_base(sbi);
-              const uint32_t a_hi0 = tmem_base + (uint32_t)kCtAccCols + 64u * (uint32_t)sa, a_lo0 = a_hi0 + 32u;
+              const uint32_t a_lo0 = a_hi0 + 32u;
 #pragma unroll
               for (int k8 = 0; k8 < 4; k8++) {
-                const uint32_t koff = k8 * 32;
-                const uint64_t b_hi = ptx::umma_desc(dhi, sb + OFF_BHI + koff), b_lo = ptx::umma_desc(dhi, sb + OFF_BLO + koff);
-                ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, b_hi, idesc, first ? 0u : 1u);
+                // the start-address field of a K-major SW128 descriptor counts 16-byte units: +2 per 8-wide k step
+                const uint64_t b_hi = b_hi0 + 2u * k8, b_lo = b_lo0 + 2u * k8;
+                ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, b_hi, idesc, k8 == 0 ? acc_on : 1u);
                 ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_lo, idesc, 1u);
                 ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_hi, idesc, 1u);
-                first = false;
               }
+              acc_on = 1u;
               ptx::umma_commit<1>(empty_a(sa));
               ptx::umma_commit<1>(empty_b(sbi));
+              a_hi0 += 64u;
+              if (++sa == kCtAStages) { sa = 0; pa ^= 1u; a_hi0 = tmem_base + (uint32_t)kCtAccCols; }
+              b_hi0 += b_step; b_lo0 += b_step;
+              if (++sbi == SB) { sbi = 0; pb ^= 1u; b_hi0 = b_hi_first; b_lo0 = b_lo_first; }
             }
             ptx::umma_commit<1>(tfull_bar(buf));
           }
@@ -285,6 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
         const uint32_t ta = t_lane + 64u * (uint32_t)sa;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
+          if (a.skip & 1) break;
           float v[16];
 #pragma unroll
           for (int j2 = 0; j2 < 8; j2++) {                 // two table entries per 128-bit broadcast load
@@ -358,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       // epilogue: out[n][co][ho][wo] = acc[co] + bias[co]; consecutive lanes = consecutive pixels
       const long long te_ = pclk();
       const int64_t p = (int64_t)tile * 128 + r;
-      if (p < a.P) {
+      if (p < a.P && !((a.skip & 2) && acc[0] != 12345.f)) {
         const int64_t n = p / HW, rem = p - n * HW;
         float* yp = a.y + n * a.CO * HW + rem;
         // the bias comes from shared memory: a global load here could alias the stores and would serialise them
@@ -461,7 +473,8 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes;
   const int groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 4) ? tuning(kTuneConvTcGroups) : 4;
   a.groups = groups_env;
-  const int dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
+  const int dbg_env = tuning(kTuneConvTcDebug) & 1;
+  a.skip = tuning(kTuneConvTcDebug) >> 1;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;

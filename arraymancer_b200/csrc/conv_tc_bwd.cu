@@ -651,30 +651,39 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
         uint32_t chain = 0;
         long long w_te = 0, w_fa = 0, w_fb = 0;
         const long long tstart = pclk();
+        // ring positions, wait parities and the position inside the accumulation chain advance by compare-and-wrap (the
+        // 64-bit `it % flush`, `it % SB`, `it / SB` of the first version were ~150 dependent instructions per stage in
+        // the single issuing thread)
+        int in_chain = 0, sa = 0, sbi = 0; uint32_t pa = 0u, pb = 0u;
+        uint32_t a_hi0 = tmem_a0;
+        const uint64_t b_first = ptx::umma_desc(dhi, smem_base), b_step = (uint64_t)(stage_bytes >> 4), b_lo_off = (uint64_t)(b_bytes >> 4);
+        uint64_t b0 = b_first;
         for (int64_t it = 0; it < T; it++) {
-          const int in_chain = (int)(it % a.flush_st);
           const int buf = chain & 1;
           if (in_chain == 0) {
             WG_TWAIT(w_te, tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
             ptx::tc_fence_after();
           }
-          const int sa = (int)(it % kWgAStages), sbi = (int)(it % SB);
-          WG_TWAIT(w_fa, full_a(sa), (uint32_t)((it / kWgAStages) & 1));
-          WG_TWAIT(w_fb, full_b(sbi), (uint32_t)((it / SB) & 1));
+          WG_TWAIT(w_fa, full_a(sa), pa);
+          WG_TWAIT(w_fb, full_b(sbi), pb);
           ptx::tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)buf * 64u;
-          const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
-          const uint32_t a_hi0 = tmem_a0 + 64u * (uint32_t)sa, a_lo0 = a_hi0 + 32u;
+          const uint32_t a_lo0 = a_hi0 + 32u;
 #pragma unroll
           for (int k8 = 0; k8 < 4; k8++) {
-            const uint64_t b_hi = ptx::umma_desc(dhi, sb + k8 * 32), b_lo = ptx::umma_desc(dhi, sb + b_bytes + k8 * 32);
+            const uint64_t b_hi = b0 + 2u * k8, b_lo = b0 + b_lo_off + 2u * k8;   // descriptor address field: 16-byte units
             ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, b_hi, idesc, (in_chain | k8) ? 1u : 0u);
             ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_lo, idesc, 1u);
             ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, b_hi, idesc, 1u);
           }
           ptx::umma_commit<1>(empty_a(sa));
           ptx::umma_commit<1>(empty_b(sbi));
-          if (in_chain == a.flush_st - 1 || it == T - 1) { ptx::umma_commit<1>(tfull_bar(buf)); chain++; }
+          if (in_chain == a.flush_st - 1 || it == T - 1) { ptx::umma_commit<1>(tfull_bar(buf)); chain++; in_chain = 0; }
+          else in_chain++;
+          a_hi0 += 64u;
+          if (++sa == kWgAStages) { sa = 0; pa ^= 1u; a_hi0 = tmem_a0; }
+          b0 += b_step;
+          if (++sbi == SB) { sbi = 0; pb ^= 1u; b0 = b_first; }
         }
         if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_te; a.dbg[2] = w_fa; a.dbg[3] = w_fb; }
       }

@@ -147,6 +147,113 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters) {
   if (warp == 1) ptx::tmem_dealloc<CG>(tmem, 512);
 }
 
+// The issue pattern of the implicit-GEMM conv kernels, piece by piece (what does the single issuing thread pay per k block
+// of 12 MMAs?).  PAT bit 0: three MMAs per k8 step on alternating A columns / B planes (3xTF32) instead of one operand pair;
+// bit 1: two tcgen05.commit per k block (operand-stage releases); bit 2: two mbarrier waits (already complete) + fence per
+// k block; bit 3: accumulation chains of 2 k blocks on alternating accumulators, one more commit per chain; bit 4: 16 KB
+// per k block bulk-copied from a 256 KB L2-resident buffer into a 4-deep shared-memory ring (the weight stream of the
+// conv kernels: every SM re-reads the same packed weights for every tile).
+template <int PAT>
+__global__ void __launch_bounds__(384, 1) umma_pattern_kernel(int iters, const float* __restrict__ gsrc) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_hi_s = base, b_lo_s = base + 8192, bar = base + 16384, bar_e = bar + 8, bar_f = bar + 24, slot = bar + 40;
+  const uint32_t bar_t = bar + 64, ring = base + 32768;      // bit 4: 4 transaction barriers + 4 x 16 KB landing ring
+  for (uint32_t i = threadIdx.x; i < 16384 / 4; i += blockDim.x) {
+    uint32_t x = i * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4 * i), "f"(ptx::to_tf32_rna(((int)(x & 0xffff) - 32768) * (1.0f / 32768.0f))));
+  }
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::mbar_init(bar, 1); ptx::mbar_init(bar_e, 1); ptx::mbar_init(bar_e + 8, 1); ptx::mbar_init(bar_f, 1);
+    for (int q = 0; q < 4; q++) ptx::mbar_init(bar_t + 8 * q, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<1>(slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (warp == 0 && ptx::elect_one()) {
+    const uint64_t dhi = ptx::umma_desc_hi(1024, 128);
+    const uint32_t idesc = ptx::umma_idesc_tf32(128, 64u);
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; it++) {                      // one iteration = one k block of 32
+      if (PAT & 16) {
+        const int sq = it & 3;
+        if (it >= 4) ptx::mbar_wait(bar_t + 8 * sq, (uint32_t)(((it >> 2) - 1) & 1));      // the copy issued 4 k blocks ago has landed
+        ptx::mbar_arrive_expect_tx(bar_t + 8 * sq, 16384u);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ring + 16384u * sq), "l"(gsrc + (size_t)(it & 15) * 4096), "r"(16384u), "r"(bar_t + 8 * sq) : "memory");
+      }
+      if (PAT & 4) {
+        ptx::mbar_wait(bar_f, 1u);                            // fresh barrier, parity 1: returns at once
+        ptx::mbar_wait(bar_f, 1u);
+        ptx::tc_fence_after();
+      }
+      const uint32_t d = tmem + ((PAT & 8) ? (uint32_t)(((it >> 1) & 1) * 64) : 0u);
+      const uint32_t a_hi0 = tmem + 128u + 64u * (uint32_t)(it % 6), a_lo0 = a_hi0 + 32u;
+#pragma unroll
+      for (int k8 = 0; k8 < 4; k8++) {
+        const uint64_t bh = ptx::umma_desc(dhi, b_hi_s + k8 * 32), bl = ptx::umma_desc(dhi, b_lo_s + k8 * 32);
+        const uint32_t first = ((PAT & 8) ? ((it & 1) == 0 && k8 == 0) : (it == 0 && k8 == 0)) ? 0u : 1u;
+        if (PAT & 1) {
+          ptx::umma_tf32_ts(d, a_lo0 + 8u * k8, bh, idesc, first);
+          ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, bl, idesc, 1u);
+          ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, bh, idesc, 1u);
+        } else {
+          ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, bh, idesc, first);
+          ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, bh, idesc, 1u);
+          ptx::umma_tf32_ts(d, a_hi0 + 8u * k8, bh, idesc, 1u);
+        }
+      }
+      if (PAT & 2) { ptx::umma_commit<1>(bar_e); ptx::umma_commit<1>(bar_e + 8); }
+      if ((PAT & 8) && (it & 1)) ptx::umma_commit<1>(bar_e);
+      if ((it & 15) == 15) {                                  // bound the queue like the microbenchmark: wait every 192 MMAs
+        ptx::umma_commit<1>(bar);
+        ptx::mbar_wait(bar, ph);
+        ph ^= 1;
+      }
+    }
+  }
+  // bit 5: warps 4-7 write the operand stages like the gather groups (one 128 x 64 stage per ~k block), bit 6: warps 8-11
+  // read 64 accumulator columns every other k block like the accumulate warps — concurrent tensor-memory traffic
+  if ((PAT & 32) && warp >= 4 && warp < 8) {
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128u;
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = threadIdx.x * 7919u + j;
+    for (int it = 0; it < iters; it++) {
+      const uint32_t ta = t_lane + 64u * (uint32_t)(it % 6);
+      ptx::tmem_st_32x16(ta, v); ptx::tmem_st_32x16(ta + 16u, v); ptx::tmem_st_32x16(ta + 32u, v); ptx::tmem_st_32x16(ta + 48u, v);
+      ptx::tmem_st_wait();
+      __nanosleep(150);
+    }
+  }
+  if ((PAT & 64) && warp >= 8 && warp < 12) {
+    const uint32_t t0 = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc = 0.f;
+    for (int it = 0; it < iters / 2; it++) {
+      uint32_t r0[32];
+      ptx::tmem_ld_32x32(t0 + (uint32_t)((it & 1) * 64), r0); ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i++) acc += __uint_as_float(r0[i]);
+      ptx::tmem_ld_32x32(t0 + (uint32_t)((it & 1) * 64) + 32u, r0); ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i++) acc += __uint_as_float(r0[i]);
+      __nanosleep(400);
+    }
+    if (acc == 1.2345f) asm volatile("st.shared.f32 [%0], %1;" ::"r"(base), "f"(acc));
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<1>(tmem, 512);
+}
+
 template <class F>
 static int time_launch(F&& launch, int reps, float* best_ms) {
   cudaEvent_t e0, e1;
@@ -214,6 +321,26 @@ int microbench(int which, double* tops) {
       const int iters = 1 << 15;
       rc = time_launch([&] { ffma2_peak_kernel<CH><<<blocks, threads>>>((float*)scratch, iters, 1.0001f, 0.9999f); g_launch_count++; }, 3, &ms);
       ops = 4.0 * CH * (double)iters * blocks * threads;
+    } break;
+    case 20: case 21: case 23: case 27: case 31: case 32: case 33: case 34: case 35: {   // 33: + operand-stage writers, 34: + accumulator readers, 35: all   // conv issue pattern, see umma_pattern_kernel (32: all pieces + the weight stream)
+      if (!gemm_f32_tc_available()) { set_last_error("microbench: tcgen05 needs compute capability 10.x"); return AM_ERR_UNSUPPORTED; }
+      const int iters = 4096 * 4, smem = 32768 + 4 * 16384 + 1024;
+      void* gbuf = nullptr;
+      if ((rc = workspace(kWsMisc, 256 * 1024 + 1024, &gbuf))) return rc;
+      const float* gsrc = (const float*)(((uintptr_t)gbuf + 127) & ~(uintptr_t)127);
+      const void* kern = which == 20 ? (const void*)umma_pattern_kernel<0> : which == 21 ? (const void*)umma_pattern_kernel<1>
+                       : which == 23 ? (const void*)umma_pattern_kernel<3> : which == 27 ? (const void*)umma_pattern_kernel<7>
+                       : which == 31 ? (const void*)umma_pattern_kernel<15> : which == 32 ? (const void*)umma_pattern_kernel<31>
+                       : which == 33 ? (const void*)umma_pattern_kernel<15 + 32> : which == 34 ? (const void*)umma_pattern_kernel<15 + 64>
+                                                                                  : (const void*)umma_pattern_kernel<127>;
+      AM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      rc = time_launch([&] {
+        int it_arg = iters;
+        void* args[2] = {&it_arg, (void*)&gsrc};
+        cudaLaunchKernel(kern, dim3(sms), dim3(384), args, smem, 0);
+        g_launch_count++;
+      }, 3, &ms);
+      ops = 2.0 * 128.0 * 64.0 * 8.0 * 12.0 * (double)iters * sms;
     } break;
     case 5:
     case 6:

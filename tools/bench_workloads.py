@@ -165,14 +165,51 @@ def run_conv(args, emit, sampler_cls, peaks_fn, log):
     sets = [(X1, X2, G1, G2)] + [tuple(t.clone() for t in (X1, X2, G1, G2)) for _ in range(R - 1)]
     counter = [0]
 
+    def body(x1, x2, g1, g2):
+        return {"o1": D.conv2d_batch_sharded(x1, W1, B1), "o2": D.conv2d_batch_sharded(x2, W2, B2),
+                "b1": D.conv2d_backward_batch_sharded(x1, W1, B1, (0, 0), (1, 1), (1, 1), g1),
+                "b2": D.conv2d_backward_batch_sharded(x2, W2, B2, (0, 0), (1, 1), (1, 1), g2)}
+
     def step():
-        x1, x2, g1, g2 = sets[counter[0] % R]
+        res.update(body(*sets[counter[0] % R]))
         counter[0] += 1
-        res["o1"] = D.conv2d_batch_sharded(x1, W1, B1)
-        res["o2"] = D.conv2d_batch_sharded(x2, W2, B2)
-        res["b1"] = D.conv2d_backward_batch_sharded(x1, W1, B1, (0, 0), (1, 1), (1, 1), g1)
-        res["b2"] = D.conv2d_backward_batch_sharded(x2, W2, B2, (0, 0), (1, 1), (1, 1), g2)
+    # The step is ~18 short launches + 4 all-reduces: at 512 images per GPU it is bound by the host's launch rate, not by the
+    # kernels.  Capture it once per input copy in a CUDA graph (kernels of this library + the NCCL all-reduces) and replay.
+    step(); step()
+    torch.cuda.synchronize()
+    l0 = _capi.kernel_launch_count(); step(); launches_per_step = _capi.kernel_launch_count() - l0
+    graphs, graph_note = None, "eager launches"
+    if not getattr(args, "no_graph", False):
+        try:
+            _barrier(world)
+            pool = torch.cuda.graph_pool_handle()
+            graphs = []
+            for i in range(R):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, pool=pool, capture_error_mode="relaxed"):
+                    out_i = body(*sets[i])
+                graphs.append((g_, out_i))
+            graph_note = f"{R} CUDA graph(s) (one per input copy), each = the whole step incl. the NCCL all-reduces, replayed"
+        except Exception as e:  # noqa: BLE001
+            graphs = None
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {e})"
+            log(graph_note)
+        flag = torch.tensor([0 if graphs else 1], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)          # all ranks replay, or none does
+        if int(flag.item()):
+            graphs = None
+    if graphs:
+        def step():  # noqa: F811
+            g_, out_i = graphs[counter[0] % R]
+            counter[0] += 1
+            g_.replay()
+            res.update(out_i)
     ms, clocks, launches = _timed(step, args, world, rank, local_rank, dev, sampler_cls, _capi)
+    if graphs:
+        launches = launches_per_step * args.steps             # replays do not pass through the library's launch counter
+    res = {k: (tuple(t.clone() if t is not None else None for t in v) if isinstance(v, tuple) else v.clone()) for k, v in res.items()}
+    graphs = None
     del sets[1:]
     f1 = 2.0 * NB * 20 * 24 * 24 * 25
     f2 = 2.0 * NB * 50 * 8 * 8 * 500
@@ -261,6 +298,7 @@ def run_conv(args, emit, sampler_cls, peaks_fn, log):
               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
               "config": {"workload": f"LeNet conv2d cv1+cv2 forward+backward, batch {NB} (BASELINE configs[3])", "batch": NB,
                          "parallelism": f"batch split over {world} GPU(s), weights replicated, grad_kernel/grad_bias all-reduced (NCCL)",
+                         "launch": graph_note,
                          "l2": f"per-rank tensors {per_rank_bytes / 1e6:.0f} MB; the step cycles through {R} copies of its inputs "
                                f"({R * per_rank_bytes / 1e6:.0f} MB > 2 x 126 MB L2), so no step finds its operands in L2"},
               "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,

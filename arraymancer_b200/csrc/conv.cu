@@ -240,7 +240,8 @@ __global__ void wgrad_reduce_kernel(const T* part, int splits, int64_t Cout, int
 struct TableCache {
   am_conv2d_desc desc{}; int device = -1; bool valid = false;
   int2 *tabF = nullptr, *tabD = nullptr, *tabW = nullptr;
-  cudaEvent_t ready = nullptr;
+  cudaStream_t stream = nullptr;     // the stream the tables were built on: a hit needs the same stream (stream order is the
+                                     // only ordering used — no events, so the calls can be captured into CUDA graphs)
 };
 // One cache entry per DEVICE, shared by all host threads and guarded by a mutex: the tables live in the per-device
 // workspace slot kWsConvTab, so the record of what that buffer holds must be per device too (a per-thread record let a
@@ -261,18 +262,15 @@ static int get_tables(cudaStream_t st, const am_conv2d_desc& d, const ConvGeom& 
   int2* f = (int2*)base; int2* dd = f + nF; int2* w = dd + nD;
   std::lock_guard<std::mutex> lk(g_tab_mu);
   TableCache& tc = g_tab[dev];
-  const bool hit = tc.valid && tc.tabF == f && memcmp(&tc.desc, &d, sizeof(d)) == 0;
+  // conv calls of one device run on one stream at a time (include/am_b200.h): a call on another stream rebuilds the tables
+  // there (one tiny kernel) instead of waiting on an event of the first stream
+  const bool hit = tc.valid && tc.tabF == f && tc.stream == st && memcmp(&tc.desc, &d, sizeof(d)) == 0;
   if (!hit) {
     const int64_t n = g.Kc > KD ? g.Kc : KD;
-    if (tc.ready) AM_CUDA_TRY(cudaStreamWaitEvent(st, tc.ready, 0));   // order after the previous build on another stream
     conv_build_tables<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, f, dd, w);
     g_launch_count++;
     AM_CUDA_TRY(cudaGetLastError());
-    if (!tc.ready) AM_CUDA_TRY(cudaEventCreateWithFlags(&tc.ready, cudaEventDisableTiming));
-    AM_CUDA_TRY(cudaEventRecord(tc.ready, st));
-    tc.desc = d; tc.device = dev; tc.valid = true; tc.tabF = f; tc.tabD = dd; tc.tabW = w;
-  } else {
-    AM_CUDA_TRY(cudaStreamWaitEvent(st, tc.ready, 0));   // tables may have been built on another stream
+    tc.desc = d; tc.device = dev; tc.valid = true; tc.tabF = f; tc.tabD = dd; tc.tabW = w; tc.stream = st;
   }
   *tabF = f; *tabD = dd; *tabW = w;
   return AM_OK;

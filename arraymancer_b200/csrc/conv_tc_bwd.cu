@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     // global loads of stage it + 1 are in flight while stage it is split and stored (the loader is otherwise
     // latency-bound: one dependent L2 round trip per stage)
     auto fetch = [&](int64_t it, float4 (&dst)[4]) {
-      const int64_t i = it / a.spi;
+      const int64_t i = (int64_t)((uint32_t)it / (uint32_t)a.spi);      // T < 2^31 stages: 32-bit division
       const int s = (int)(it - i * a.spi);
       const int64_t n = slice + i * a.nslices;
       const int q0 = s * 32 + part * ppt;
@@ -794,14 +794,17 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
         dst[v4] = f;
       }
     };
-    float4 cur[4], nxt[4];
-    if (T > 0) fetch(0, cur);
+    // a stage is consumed in ~500 cycles (12 MMAs) but one L2 round trip takes longer: the loads of stage it + 2 are issued
+    // before stage it is split and stored (three register buffers, rotated by a 3x unrolled loop — no register copies).
+    // With a distance of one stage the MMA thread spent 37 % of its time waiting for grad_output (r02_convtc_waits.txt).
+    float4 bufA[4], bufB[4], bufC[4];
+    if (T > 0) fetch(0, bufA);
+    if (T > 1) fetch(1, bufB);
     long long w_eb = 0;
     const long long tstart = pclk();
-    for (int64_t it = 0; it < T; it++) {
-      if (it + 1 < T) fetch(it + 1, nxt);
-      const int sbi = (int)(it % SB);
-      WG_TWAIT(w_eb, empty_b(sbi), (uint32_t)((it / SB) & 1) ^ 1u);
+    int sbi = 0; uint32_t pb = 1u;
+    auto consume = [&](const float4 (&cur)[4]) {
+      WG_TWAIT(w_eb, empty_b(sbi), pb);
       const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
 #pragma unroll
       for (int v4 = 0; v4 < 4; v4++) {
@@ -822,8 +825,19 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b(sbi)) : "memory");
-#pragma unroll
-      for (int v4 = 0; v4 < 4; v4++) cur[v4] = nxt[v4];
+      if (++sbi == SB) { sbi = 0; pb ^= 1u; }
+    };
+    for (int64_t it = 0; it < T; it += 3) {
+      if (it + 2 < T) fetch(it + 2, bufC);
+      consume(bufA);
+      if (it + 1 < T) {
+        if (it + 3 < T) fetch(it + 3, bufA);
+        consume(bufB);
+      }
+      if (it + 2 < T) {
+        if (it + 4 < T) fetch(it + 4, bufB);
+        consume(bufC);
+      }
     }
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[7] = pclk() - tstart; a.dbg[8] = w_eb; }
   } else {

@@ -9,6 +9,8 @@
  * library keeps ONE set of scratch buffers per device (packed operand panels, conv partials, ...), ordered by the
  * stream of the call that uses them: calls of the same family (GEMM, conv, NN ops) on one device must be issued on
  * one stream (or be ordered by events); different devices and different families are independent.
+ * CUDA graphs: the device entries only enqueue kernels / copies on the given stream (no events, no other streams, no host
+ * synchronisation), so after one eager call has sized the scratch buffers they can be stream-captured and replayed.
  *
  * The reference-side bindings (Nim {.importc, cdecl, dynlib.}) are shown in INTEGRATION.md.
  */

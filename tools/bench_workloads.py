@@ -192,8 +192,14 @@ def run_conv(args, emit, sampler_cls, peaks_fn, log):
             graph_note = f"{R} CUDA graph(s) (one per input copy), each = the whole step incl. the NCCL all-reduces, replayed"
         except Exception as e:  # noqa: BLE001
             graphs = None
-            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {e})"
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e).splitlines()[0]})"
             log(graph_note)
+            for _ in range(3):                                   # a failed capture leaves a sticky error in the library's runtime
+                try:
+                    torch.cuda.synchronize(); body(*sets[0]); torch.cuda.synchronize()
+                    break
+                except Exception:  # noqa: BLE001
+                    pass
         flag = torch.tensor([0 if graphs else 1], device=dev)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)          # all ranks replay, or none does

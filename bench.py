@@ -251,6 +251,7 @@ def main():
                     help="N>1: 'fused' = the GEMM epilogue stores C to every GPU's copy over NVLink (symmetric memory); "
                          "'nccl' = per-chunk ncclAllGather on a second stream")
     ap.add_argument("--no-graph", action="store_true", help="conv workload: launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--graph", action="store_true", help="conv workload, N>1: replay CUDA graphs (incl. the NCCL all-reduces) too")
     ap.add_argument("--static-b", action="store_true",
                     help="sgemm: B is a constant (weight-like) operand, packed once outside the timed step")
     args = ap.parse_args()

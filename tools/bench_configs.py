@@ -5,7 +5,7 @@ here only as the checker, outside every timed region).
 
 Record layout:
   {"name", "config" (C1..C5 / "skinny"), "dtype", "shape", "ms" (median), "ms_best", "reps",
-   "achieved", "peak", "unit", "frac", "bound" ("imad"|"dmma"|"tensor"|"hbm"), "peak_source",
+   "achieved", "peak", "unit", "frac", "bound" ("imad"|"dmma"|"tensor"|"hbm"|"ffma"), "peak_source",
    "gbps" (algorithmic bytes / ms), "l2": how cache effects are excluded, "clocks": {...},
    "parity": {"ok", "kind": "bit-exact"|"rel_fro", "value", "tol", "against", "sample"}}
 Inputs follow SURVEY §8d: splitmix64 streams (seeds 42/43 C1, 7 full-range, 1234/1235 C3), the kostya generator for
@@ -147,6 +147,12 @@ def run_configs(am, orc, peaks, sampler_cls, gpu_index=0, only=None, log=None):
         except Exception as e:  # noqa: BLE001
             pipe[n] = None
             say(f"microbench {n} failed: {e}")
+    for n, i in (("ffma2_f32x2", 13), ("umma_tf32_n64_conv_issue_pattern", 31), ("umma_tf32_n64_conv_pattern_with_weight_stream", 32)):
+        try:
+            pipe[n] = _capi.microbench(i)
+        except Exception as e:  # noqa: BLE001
+            pipe[n] = None
+            say(f"microbench {n} failed: {e}")
     hbm = float(peaks.get("hbm_gbs", 6454.3))
     tf32x3 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0))) / 6.0
     P = {"f32": (tf32x3, "TFLOP/s", "tensor", "MEASURED_PEAKS bf16_tflops_sustained / 2 / 3 (3xTF32)"),
@@ -268,12 +274,16 @@ def run_configs(am, orc, peaks, sampler_cls, gpu_index=0, only=None, log=None):
             orc.gemm_strided(1, A.cpu().numpy(), B.cpu().numpy(), 0, wantc)
             rel = _rel(got, wantc)
             bytes_ = 4 * (m * n + n * n + m * n)
+            # thin dimension <= 16: 2*m flop per 4-byte element of B is below the FFMA ridge -> DRAM-bound, reported in GB/s;
+            # m = 64: 128 flop per element, FFMA-bound on the exact-fp32 SIMT kernel -> reported against the FFMA pipe
+            ffma_bound = m > 16 and pipe.get("ffma_f32")
             recs.append(_rec(f"skinny_f32_M{m}_N{n}_K{n}", "skinny", "f32", [m, n, n], ms, best, reps, clocks, 2.0 * m * n * n,
-                             bytes_, hbm, 1e12, "GB/s", "hbm", "MEASURED_PEAKS hbm_gbs",
+                             bytes_, pipe["ffma_f32"] if ffma_bound else hbm, 1e12, "TFLOP/s" if ffma_bound else "GB/s",
+                             "ffma" if ffma_bound else "hbm", "am_microbench 0 (FFMA), this run" if ffma_bound else "MEASURED_PEAKS hbm_gbs",
                              {"ok": bool(rel <= 5e-6), "kind": "rel_fro", "value": rel, "tol": 5e-6,
                               "against": "oracle.gemm_strided", "sample": "all rows"}, BIG,
                              {"note": "M rows against a 1 GiB B: the product streams B once (DRAM-bound)"}))
-            say(f"skinny M={m}: {ms:.3f} ms {recs[-1]['achieved']:.0f} GB/s frac {recs[-1]['frac']:.3f} rel {rel:.2e}")
+            say(f"skinny M={m}: {ms:.3f} ms {recs[-1]['achieved']:.0f} {recs[-1]['unit']} frac {recs[-1]['frac']:.3f} rel {rel:.2e}")
             # the transposed twin: tall A (n x n) times a skinny B (n x m), i.e. the gemv-like `A * v` of the reference
             Bs = gen_matrix_chunked("u11", n, m, 1237, dev, torch.float32)
             Cs = torch.empty((n, m), device=dev, dtype=torch.float32)
@@ -283,11 +293,12 @@ def run_configs(am, orc, peaks, sampler_cls, gpu_index=0, only=None, log=None):
             orc.gemm_strided(1, B.cpu().numpy(), Bs.cpu().numpy(), 0, wantc)
             rel = _rel(got, wantc)
             recs.append(_rec(f"skinny_f32_M{n}_N{m}_K{n}", "skinny", "f32", [n, m, n], ms, best, reps, clocks, 2.0 * m * n * n,
-                             bytes_, hbm, 1e12, "GB/s", "hbm", "MEASURED_PEAKS hbm_gbs",
+                             bytes_, pipe["ffma_f32"] if ffma_bound else hbm, 1e12, "TFLOP/s" if ffma_bound else "GB/s",
+                             "ffma" if ffma_bound else "hbm", "am_microbench 0 (FFMA), this run" if ffma_bound else "MEASURED_PEAKS hbm_gbs",
                              {"ok": bool(rel <= 5e-6), "kind": "rel_fro", "value": rel, "tol": 5e-6,
                               "against": "oracle.gemm_strided", "sample": "all rows"}, BIG,
                              {"note": "1 GiB A against N columns (N = 1: the matrix-vector product of `*`)"}))
-            say(f"skinny N={m}: {ms:.3f} ms {recs[-1]['achieved']:.0f} GB/s frac {recs[-1]['frac']:.3f} rel {rel:.2e}")
+            say(f"skinny N={m}: {ms:.3f} ms {recs[-1]['achieved']:.0f} {recs[-1]['unit']} frac {recs[-1]['frac']:.3f} rel {rel:.2e}")
             del A, C, Bs, Cs
         del B
         torch.cuda.empty_cache()

@@ -179,7 +179,10 @@ def run_conv(args, emit, sampler_cls, peaks_fn, log):
     torch.cuda.synchronize()
     l0 = _capi.kernel_launch_count(); step(); launches_per_step = _capi.kernel_launch_count() - l0
     graphs, graph_note = None, "eager launches"
-    if not getattr(args, "no_graph", False):
+    # multi-rank: opt-in (--graph) — replay works (2 GPUs: 0.512 vs 0.522 ms eager) but a process that holds CUDA graphs with
+    # captured NCCL kernels hung in its teardown on the 2-GPU box; single GPU: on by default (0.88 vs 1.05 ms eager)
+    use_graph = (not getattr(args, "no_graph", False)) and (world == 1 or getattr(args, "graph", False))
+    if use_graph:
         try:
             _barrier(world)
             pool = torch.cuda.graph_pool_handle()
@@ -194,9 +197,9 @@ def run_conv(args, emit, sampler_cls, peaks_fn, log):
             graphs = None
             graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e).splitlines()[0]})"
             log(graph_note)
-            for _ in range(3):                                   # a failed capture leaves a sticky error in the library's runtime
-                try:
-                    torch.cuda.synchronize(); body(*sets[0]); torch.cuda.synchronize()
+            for _ in range(3):                                   # a failed capture leaves a sticky error in the library's runtime:
+                try:                                             # flush it with collective-free work (the peers are not in this branch)
+                    torch.cuda.synchronize(); D.conv2d_batch_sharded(sets[0][0], W1, B1); torch.cuda.synchronize()
                     break
                 except Exception:  # noqa: BLE001
                     pass

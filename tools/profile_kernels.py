@@ -1,5 +1,5 @@
 """Launch each kernel family once (after a warm-up) so `ncu` can capture it.
-usage: python tools/profile_kernels.py [simt|tc|conv|all]"""
+usage: python tools/profile_kernels.py [simt|tc|conv|skinny|all]"""
 import os
 import sys
 
@@ -49,4 +49,13 @@ if what in ("conv", "convtc", "all"):
         for _ in range(reps):
             out = am.conv2d(X, W, B)
             am.conv2d_backward(X, W, B, (0, 0), (1, 1), (1, 1), torch.ones_like(out))
+        torch.cuda.synchronize()
+if what == "skinny":
+    n = 16384
+    for shape in ((16, n, n), (n, 16, n)):
+        M, N, K = shape
+        A = torch.rand(M, K, device="cuda") * 2 - 1; B = torch.rand(K, N, device="cuda") * 2 - 1
+        C = torch.empty(M, N, device="cuda")
+        for _ in range(reps):
+            am.gemm_strided(1, A, B, 0, C)
         torch.cuda.synchronize()

@@ -65,6 +65,7 @@ struct ConvTcArgs {
   uint32_t raw_bytes;   // bytes of one raw-image buffer (max images a tile touches * CHW * 4, rounded up)
   long long* dbg;       // optional: per-role wait-cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
   int relu;             // fused activation: y = max(0, conv + bias)
+  int hi_res;           // the hi weight plane of every k block stays resident in shared memory; only the lo plane is streamed
   int skip;             // experiments (knob convtc_debug >> 1): bit 0 = gather warps skip their loads / stores to TMEM, bit 1 = no output stores
 };
 
@@ -115,10 +116,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int SB = a.stages;                                              // weight ring depth
   const uint32_t b_bytes = (uint32_t)a.NP * 128u;                     // one weight plane per stage
-  const uint32_t stage_bytes = 2u * b_bytes;
+  // ring stage: [hi plane | lo plane], or the lo plane alone when the hi planes of all k blocks are resident (hi_res): the
+  // weight stream from L2 is what slows the MMAs down (profiles/r02_conv_tc_issue_analysis.md), this halves it
+  const uint32_t stage_bytes = a.hi_res ? b_bytes : 2u * b_bytes;
   auto stage_base = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
-  const uint32_t OFF_BHI = 0, OFF_BLO = b_bytes;
-  const uint32_t raw_base = smem_base + (uint32_t)SB * stage_bytes;     // two raw-image buffers
+  const uint32_t OFF_BHI = 0, OFF_BLO = a.hi_res ? 0u : b_bytes;
+  const uint32_t hi_base = smem_base + (uint32_t)SB * stage_bytes;      // hi_res: [kblocks][NP x 32] resident hi planes
+  const uint32_t raw_base = hi_base + (a.hi_res ? (uint32_t)a.kblocks * b_bytes : 0u);     // two raw-image buffers
   const uint32_t bar_base = raw_base + 2u * a.raw_bytes;
   auto full_a = [&](int s) { return bar_base + 8u * s; };               // 6
   auto empty_a = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
@@ -129,6 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   auto raw_full = [&](int b) { return bar_base + 8u * (32 + b); };
   auto raw_empty = [&](int b) { return bar_base + 8u * (34 + b); };
   const uint32_t tmem_slot = bar_base + 8u * 36;
+  const uint32_t hi_full = bar_base + 8u * 37;                          // hi_res: the resident planes have landed
   const uint32_t bias_s = bar_base + 8u * 38;                           // float bias[64] (zero when there is none)
   const uint32_t tab_s = bias_s + 256u;                                 // int2 tab[kblocks*32]
 
@@ -154,6 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4);
       ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G);
     }
+    ptx::mbar_init(hi_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, tmem_cols);
@@ -184,12 +190,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
         int s = 0; uint32_t ph = 1u;                  // ring position and wait parity, advanced without divisions
         long long w_eb = 0;
         const long long tstart = pclk();
+        if (a.hi_res) {
+          ptx::mbar_arrive_expect_tx(hi_full, (uint32_t)nkb * b_bytes);
+          for (int kb = 0; kb < nkb; kb++) ptx::tma_load_2d(hi_base + (uint32_t)kb * b_bytes, &tmWhi, hi_full, kb * 32, 0);
+        }
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
           for (int kb = 0; kb < nkb; kb++) {
             CT_TWAIT(w_eb, empty_b(s), ph);
             const uint32_t sb = stage_base(s);
-            ptx::mbar_arrive_expect_tx(full_b(s), 2 * b_bytes);
-            ptx::tma_load_2d(sb + OFF_BHI, &tmWhi, full_b(s), kb * 32, 0);
+            ptx::mbar_arrive_expect_tx(full_b(s), stage_bytes);
+            if (!a.hi_res) ptx::tma_load_2d(sb + OFF_BHI, &tmWhi, full_b(s), kb * 32, 0);
             ptx::tma_load_2d(sb + OFF_BLO, &tmWlo, full_b(s), kb * 32, 0);
             if (++s == SB) { s = 0; ph ^= 1u; }
           }
@@ -208,12 +218,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
         // same issue pattern alone sustains 38, am_microbench 27/31)
         int sa = 0, sbi = 0; uint32_t pa = 0u, pb = 0u;
         uint32_t a_hi0 = tmem_base + (uint32_t)kCtAccCols;
-        uint64_t b_hi0 = ptx::umma_desc(dhi, stage_base(0) + OFF_BHI), b_lo0 = ptx::umma_desc(dhi, stage_base(0) + OFF_BLO);
-        const uint64_t b_hi_first = b_hi0, b_lo_first = b_lo0, b_step = (uint64_t)(stage_bytes >> 4);
+        uint64_t b_hi0 = ptx::umma_desc(dhi, a.hi_res ? hi_base : stage_base(0) + OFF_BHI), b_lo0 = ptx::umma_desc(dhi, stage_base(0) + OFF_BLO);
+        const uint64_t b_hi_first = b_hi0, b_lo_first = b_lo0, b_step = (uint64_t)(stage_bytes >> 4), b_step_hi = (uint64_t)(b_bytes >> 4);
+        if (a.hi_res) ptx::mbar_wait(hi_full, 0u);
         long long w_te = 0, w_fa = 0, w_fb = 0;
         const long long tstart = pclk();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
           int kb = 0;
+          if (a.hi_res) b_hi0 = b_hi_first;                   // resident planes are indexed by the k block of the tile
           for (int c = 0; c < chains_per_tile; c++, chain++) {
             const int buf = chain & 1;
             CT_TWAIT(w_te, tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
@@ -238,8 +250,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
               ptx::umma_commit<1>(empty_b(sbi));
               a_hi0 += 64u;
               if (++sa == kCtAStages) { sa = 0; pa ^= 1u; a_hi0 = tmem_base + (uint32_t)kCtAccCols; }
-              b_hi0 += b_step; b_lo0 += b_step;
-              if (++sbi == SB) { sbi = 0; pb ^= 1u; b_hi0 = b_hi_first; b_lo0 = b_lo_first; }
+              b_lo0 += b_step;
+              b_hi0 += a.hi_res ? b_step_hi : b_step;
+              if (++sbi == SB) { sbi = 0; pb ^= 1u; b_lo0 = b_lo_first; if (!a.hi_res) b_hi0 = b_hi_first; }
             }
             ptx::umma_commit<1>(tfull_bar(buf));
           }
@@ -431,9 +444,14 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   const int64_t HWo = (int64_t)v.HO * v.WO;
   const int64_t max_imgs = (128 % HWo == 0) ? 128 / HWo : 127 / HWo + 2;      // images one 128-pixel tile can touch
   const int64_t raw_bytes = round_up(max_imgs * CHW * 4, 128);
-  const size_t stage_bytes = 2 * (size_t)NP * 128;
-  const size_t fixed = 1024 + 8 * 38 + 256 + (size_t)Kpad * 8 + 64 + 2 * (size_t)raw_bytes;
+  const size_t b_bytes = (size_t)NP * 128;
+  size_t stage_bytes = 2 * b_bytes;
+  size_t fixed = 1024 + 8 * 38 + 256 + (size_t)Kpad * 8 + 64 + 2 * (size_t)raw_bytes;
   if (fixed + 2 * stage_bytes > 227 * 1024) return AM_OK;
+  // resident hi planes (+ a ring of >= 4 lo planes) when they fit: halves the weight stream every tile re-reads from L2
+  const size_t hi_bytes = (size_t)nkb * b_bytes;
+  const bool hi_res = tuning(kTuneConvTcHiRes) != 0 && fixed + hi_bytes + 4 * b_bytes <= 227 * 1024;
+  if (hi_res) { stage_bytes = b_bytes; fixed += hi_bytes; }
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kCtMaxBStages) stages = kCtMaxBStages;
   const bool checked = v.padH != 0 || v.padW != 0;
@@ -470,7 +488,7 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   }
   ConvTcArgs a{};
   a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N; a.relu = v.relu;
-  a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes;
+  a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes; a.hi_res = hi_res ? 1 : 0;
   const int groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 4) ? tuning(kTuneConvTcGroups) : 4;
   a.groups = groups_env;
   const int dbg_env = tuning(kTuneConvTcDebug) & 1;

@@ -15,9 +15,9 @@
 //                 see gemm_f32_tc.cu)
 //   warp 2        TMEM allocation
 //   warp 3        bulk-copy producer for the raw images of the NEXT tile (double-buffered)
-//   warps 4..19   `groups` (<= 4) gather groups of 128 threads (thread r <-> output pixel r <-> TMEM lane r); group g
-//                 expands the k blocks g, g + groups, ... so several of the 6 operand stages are being filled at once
-//   last 4 warps  drain finished chains (tcgen05.ld) into register accumulators with round-to-nearest adds, then the
+//   warps 4..15   `groups` (<= 3) gather groups of 128 threads (thread r <-> output pixel r <-> TMEM lane r); group g
+//                 expands the k blocks g, g + groups, ... so several of the 4 operand stages are being filled at once
+//   last 8 warps  (lane quarter x column half) drain finished chains (tcgen05.ld) into register accumulators with round-to-nearest adds, then the
 //                 epilogue: + bias, NCHW stores (lanes = consecutive pixels: coalesced)
 #include <cuda.h>
 #include <cstdio>
@@ -103,8 +103,14 @@ __global__ void conv_tc_table_kernel(int2* tab, int K, int Kpad, int kH, int kW,
 }
 
 // CHECK = the convolution has padding: taps outside the image read as zero (bounds test per element)
-constexpr int kCtAStages = 6;             // im2col operand stages in tensor memory: 64 columns each (hi 32 | lo 32)
-constexpr int kCtAccCols = 128;           // two accumulator buffers of up to 64 columns
+// Tensor-memory plan (512 columns): FOUR accumulator buffers of up to 64 columns + four im2col operand stages of 64 columns
+// (hi 32 | lo 32).  An accumulation chain is only 2 k blocks = 24 MMAs (~1000 cycles) long for fp32 accuracy, and draining
+// one (barrier wake-up, two dependent tcgen05.ld round trips, 64 adds, arrive) takes about as long: with two buffers the
+// tensor pipe waited for the drain of chain c-2 before it could start chain c (measured: 134 us at chains of 2 k blocks,
+// 101 us at chains of 8 — at four times the rounding error).  Four buffers let the MMAs run three chains ahead.
+constexpr int kCtAStages = 4;
+constexpr int kCtAccBufs = 4;
+constexpr int kCtAccCols = 64 * kCtAccBufs;
 constexpr int kCtMaxBStages = 8;
 
 #define CT_TWAIT(counter, bar, ph) do { const long long t0_ = pclk(); ptx::mbar_wait(bar, ph); counter += pclk() - t0_; } while (0)
@@ -124,12 +130,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   const uint32_t hi_base = smem_base + (uint32_t)SB * stage_bytes;      // hi_res: [kblocks][NP x 32] resident hi planes
   const uint32_t raw_base = hi_base + (a.hi_res ? (uint32_t)a.kblocks * b_bytes : 0u);     // two raw-image buffers
   const uint32_t bar_base = raw_base + 2u * a.raw_bytes;
-  auto full_a = [&](int s) { return bar_base + 8u * s; };               // 6
-  auto empty_a = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
-  auto full_b = [&](int s) { return bar_base + 8u * (12 + s); };        // 8
-  auto empty_b = [&](int s) { return bar_base + 8u * (20 + s); };       // 8
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (28 + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (30 + b); };
+  auto full_a = [&](int s) { return bar_base + 8u * s; };               // 4
+  auto empty_a = [&](int s) { return bar_base + 8u * (4 + s); };        // 4
+  auto full_b = [&](int s) { return bar_base + 8u * (8 + s); };         // 8
+  auto empty_b = [&](int s) { return bar_base + 8u * (16 + s); };       // 8
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (24 + b); };     // 4
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (28 + b); };    // 4
   auto raw_full = [&](int b) { return bar_base + 8u * (32 + b); };
   auto raw_empty = [&](int b) { return bar_base + 8u * (34 + b); };
   const uint32_t tmem_slot = bar_base + 8u * 36;
@@ -141,8 +147,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   const uint32_t lane = ptx::lane_id();
   const int nkb = a.kblocks;
   const int G = a.groups;
-  const int acc_warp0 = 20;                               // the last four of the 24 launched warps
-  const uint32_t tmem_cols = 512u;                        // accumulators (128) + 6 operand stages (384)
+  const int acc_warp0 = 16;                               // the last eight of the 24 launched warps
+  const uint32_t tmem_cols = 512u;                        // accumulators (256) + 4 operand stages (256)
   const int64_t HW = (int64_t)a.HO * a.WO;
 
   if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tensormap(&tmWhi); ptx::prefetch_tensormap(&tmWlo); }
@@ -155,21 +161,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       ptx::mbar_init(full_b(s), 1);        // TMA transaction bytes
       ptx::mbar_init(empty_b(s), 1);       // tcgen05.commit
     }
-    for (int b = 0; b < 2; b++) {
-      ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4);
-      ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G);
-    }
+    for (int b = 0; b < kCtAccBufs; b++) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), a.NP > 32 ? 8 : 4); }
+    for (int b = 0; b < 2; b++) { ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G); }
     ptx::mbar_init(hi_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < nkb * 32; i += blockDim.x) {            // k-decode table -> shared memory
-    const int2 e = a.tab[i];
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab_s + 8u * i), "r"(e.x), "r"(e.y));
-  }
   if (threadIdx.x < 64) {
     const float bv = (a.bias != nullptr && (int)threadIdx.x < a.CO) ? a.bias[threadIdx.x] : 0.f;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * threadIdx.x), "f"(bv));
+  }
+  for (int i = threadIdx.x; i < nkb * 32; i += blockDim.x) {            // k-decode table -> shared memory
+    const int2 e = a.tab[i];
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab_s + 8u * i), "r"(e.x), "r"(e.y));
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -180,8 +184,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
   const int flush = a.flush_kb;
   const int chains_per_tile = (nkb + flush - 1) / flush;
 
-  // register budget (24 warps launched at 80 per thread = 61440): control warps 56, up to 16 gather warps 72 (idle
-  // ones 40), accumulate warps 136  (7168 + 36864 + 17408 = 61440)
+  // register budget (24 warps launched at 80 per thread = 61440): control warps 56, up to 12 gather warps 72 (idle ones 40),
+  // eight accumulate warps 104  (7168 + 27648 + 26624 = 61440)
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
@@ -227,8 +231,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
           int kb = 0;
           if (a.hi_res) b_hi0 = b_hi_first;                   // resident planes are indexed by the k block of the tile
           for (int c = 0; c < chains_per_tile; c++, chain++) {
-            const int buf = chain & 1;
-            CT_TWAIT(w_te, tempty_bar(buf), ((chain >> 1) & 1u) ^ 1u);
+            const int buf = chain & (kCtAccBufs - 1);
+            CT_TWAIT(w_te, tempty_bar(buf), ((chain / kCtAccBufs) & 1u) ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)buf * 64u;
             const int kb_end = (kb + flush < nkb) ? kb + flush : nkb;
@@ -347,35 +351,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else {
     // ===================== accumulate / epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
-    const int q = warp & 3;
+    // Eight warps: warp (q, half) owns TMEM lanes 32q..32q+31 (pixels) and accumulator columns 32*half..32*half+31 (output
+    // channels).  A chain of 2 k blocks is executed in ~1000 cycles and has to be drained in less: one tcgen05.ld + 32 adds
+    // per warp (four warps x 64 columns took two dependent loads and twice the adds: the tensor pipe waited for them)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3, half = (warp - acc_warp0) >> 2;
     const int r = q * 32 + (int)lane;                      // TMEM lane = pixel row of the tile
+    const int c_lo = half * 32;
+    if (c_lo < a.NP) {
     uint32_t chain = 0;
     long long w_tf = 0, w_ep = 0;
     const long long tstart = pclk();
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      float acc[64];
+      float acc[32];
 #pragma unroll
-      for (int i = 0; i < 64; i++) acc[i] = 0.f;
+      for (int i = 0; i < 32; i++) acc[i] = 0.f;
       for (int c = 0; c < chains_per_tile; c++, chain++) {
-        const int buf = chain & 1;
-        CT_TWAIT(w_tf, tfull_bar(buf), (chain >> 1) & 1u);
+        const int buf = chain & (kCtAccBufs - 1);
+        CT_TWAIT(w_tf, tfull_bar(buf), (chain / kCtAccBufs) & 1u);
         ptx::tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 64u;
-        {
-          uint32_t r0[32];
-          ptx::tmem_ld_32x32(t0, r0);
-          ptx::tmem_ld_wait();
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + c_lo), r0);
+        ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
-        }
-        if (a.NP > 32) {
-          uint32_t r1[32];
-          ptx::tmem_ld_32x32(t0 + 32, r1);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i]));
-        }
+        for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
@@ -385,17 +384,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       const int64_t p = (int64_t)tile * 128 + r;
       if (p < a.P && !((a.skip & 2) && acc[0] != 12345.f)) {
         const int64_t n = p / HW, rem = p - n * HW;
-        float* yp = a.y + n * a.CO * HW + rem;
+        float* yp = a.y + (n * a.CO + c_lo) * HW + rem;
         // the bias comes from shared memory: a global load here could alias the stores and would serialise them
 #pragma unroll
-        for (int c4 = 0; c4 < 16; c4++) {
-          if (c4 * 4 < a.CO) {
+        for (int c4 = 0; c4 < 8; c4++) {
+          if (c_lo + c4 * 4 < a.CO) {
             float b0, b1, b2, b3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_s + 16u * c4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_s + 4u * (uint32_t)c_lo + 16u * c4));
             const float bb[4] = {b0, b1, b2, b3};
 #pragma unroll
             for (int e = 0; e < 4; e++)
-              if (c4 * 4 + e < a.CO) {
+              if (c_lo + c4 * 4 + e < a.CO) {
                 const float v = __fadd_rn(acc[c4 * 4 + e], bb[e]);
                 yp[(c4 * 4 + e) * HW] = (a.relu && v <= 0.f) ? 0.f : v;
               }
@@ -404,7 +403,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant_
       }
       w_ep += pclk() - te_;
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 640) { a.dbg[11] = pclk() - tstart; a.dbg[12] = w_tf; a.dbg[13] = w_ep; }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[11] = pclk() - tstart; a.dbg[12] = w_tf; a.dbg[13] = w_ep; }
+    }
   }
 
   __syncwarp();
@@ -489,7 +489,7 @@ static int run_conv_tc(cudaStream_t st, const ConvTcView& v, bool* done) {
   ConvTcArgs a{};
   a.x = v.x; a.bias = v.bias; a.y = v.y; a.tab = tab; a.P = P; a.N = v.N; a.relu = v.relu;
   a.CHW = (int)CHW; a.stages = stages; a.raw_bytes = (uint32_t)raw_bytes; a.hi_res = hi_res ? 1 : 0;
-  const int groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 4) ? tuning(kTuneConvTcGroups) : 4;
+  const int groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 3) ? tuning(kTuneConvTcGroups) : 3;
   a.groups = groups_env;
   const int dbg_env = tuning(kTuneConvTcDebug) & 1;
   a.skip = tuning(kTuneConvTcDebug) >> 1;

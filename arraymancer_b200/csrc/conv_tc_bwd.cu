@@ -705,15 +705,19 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     }
     long long w_rf = 0, w_ea = 0;
     const long long tstart = pclk();
+    // stage counters advance by compare-and-wrap (no 64-bit `it % G`, `it % stages`, `it / stages` per stage and thread)
+    int turn = 0, sa_run = 0; uint32_t pa_run = 1u;              // whose stage this is | ring position | wait parity of the ring lap
     for (int64_t i = 0; i < nimg; i++) {
       const int b = (int)(i & 1);
       WG_TWAIT(w_rf, raw_full(b), (uint32_t)((i >> 1) & 1));      // every group waits for every image (keeps the phases of raw_empty in step)
       const uint32_t xb = raw_base + (uint32_t)b * a.raw_bytes + (uint32_t)(base * 4);
       for (int s = 0; s < a.spi; s++) {
-        const int64_t it = i * a.spi + s;
-        if ((int)(it % G) != g) continue;
-        const int sa = (int)(it % kWgAStages);
-        WG_TWAIT(w_ea, empty_a(sa), (uint32_t)((it / kWgAStages) & 1) ^ 1u);
+        const int sa = sa_run; const uint32_t pa = pa_run;
+        const bool mine = turn == g;
+        if (++turn == G) turn = 0;
+        if (++sa_run == kWgAStages) { sa_run = 0; pa_run ^= 1u; }
+        if (!mine) continue;
+        WG_TWAIT(w_ea, empty_a(sa), pa);
         ptx::tc_fence_after();
         const uint32_t ta = t_lane + 64u * (uint32_t)sa;
         const int q0 = s * 32;
@@ -856,19 +860,21 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       WG_TWAIT(w_tf, tfull_bar(buf), (uint32_t)((c >> 1) & 1));
       ptx::tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)buf * 64u;
-      {
+      if (a.NP > 32) {                                       // both halves in flight before the one wait
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(t0, r0);
+        ptx::tmem_ld_32x32(t0 + 32, r1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i]));
+      } else {
         uint32_t r0[32];
         ptx::tmem_ld_32x32(t0, r0);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
-      }
-      if (a.NP > 32) {
-        uint32_t r1[32];
-        ptx::tmem_ld_32x32(t0 + 32, r1);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) acc[32 + i] = __fadd_rn(acc[32 + i], __uint_as_float(r1[i]));
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -25,6 +25,7 @@ enum TuneKey : int {
   kTuneSimtVecLoad,        // "simt_vec_load": 128-bit global loads along a unit-stride operand dimension in the SIMT GEMM (default 1)
   kTuneDmmaTma,            // "dmma_tma": TMA-fed 16-warp DMMA kernel for unit-stride float64 operands (default 1; 0: register-staged kernel)
   kTuneConvTcHiRes,        // "convtc_hi_resident": tcgen05 conv forward keeps the hi weight planes resident in shared memory (default 1)
+  kTuneConvTcFlushKb,      // "convtc_flush_kb": k blocks (of 32) per TMEM accumulation chain of the tcgen05 conv forward (default 4)
   kTuneCount
 };
 int tuning(int key);

@@ -46,7 +46,7 @@ AM_API int am_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Reference scratch is per call (laser/.../gemm_tiling.nim:266-270,326); here it is cached. */
 AM_API int am_shutdown(void);
 /* Tuning knobs, set explicitly by the caller (process-wide atomics; the library reads NO environment variables):
- *   "tc_flush_kb" (2)  k-blocks of 32 per tensor-core accumulation chain of the 3xTF32 kernels
+ *   "tc_flush_kb" (2)  k-blocks of 32 per tensor-core accumulation chain of the 3xTF32 GEMM and conv wgrad kernels
  *   "tc_group" (8)     rasterisation group of the persistent GEMM (< 0: groups of N tiles)
  *   "tc_sync" (1)      per-wave grid barrier of the persistent GEMM
  *   "pack_scalar" (0)  force the scalar split/pack kernel
@@ -54,6 +54,9 @@ AM_API int am_shutdown(void);
  *   "convtc_groups" (0 = kernel default), "convtc_debug" (0), "convtc_dgrad_gather" (0): tcgen05 conv kernels
  *   "simt_vec_load" (1)  128-bit global accesses along a unit-stride operand dimension in the SIMT GEMM
  *   "dmma_tma" (1)     TMA-fed 16-warp DMMA kernel for unit-stride float64 operands (0: register-staged 8-warp kernel)
+ *   "convtc_hi_resident" (1)  tcgen05 conv forward keeps the hi weight planes resident in shared memory when they fit
+ *   "convtc_flush_kb" (4)  k-blocks of 32 per accumulation chain of the tcgen05 conv forward (cv2: 7e-7 rel. Frobenius at 4,
+ *                      4e-7 at 2 and 12 % slower); "convtc_debug" bits 1-2 switch pieces of that kernel off (experiments only)
  * Unknown names return AM_ERR_INVALID. */
 AM_API int am_set_tuning(const char* name, int value);
 AM_API int am_get_tuning(const char* name, int* value);

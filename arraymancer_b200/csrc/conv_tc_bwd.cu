@@ -511,7 +511,7 @@ int conv2d_dgrad_col2im_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t
     if (r != CUDA_SUCCESS) { set_last_error("conv dgrad tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AM_ERR_CUDA; }
   }
   int dbg_env;
-  dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
+  dbg_env = tuning(kTuneConvTcDebug) & 1;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;
@@ -564,9 +564,11 @@ struct WgradTcArgs {
   int SB;               // depth of the gout ring
   int groups;           // gather groups (of 128 threads), <= 3
   uint32_t raw_bytes;   // bytes of one staged-input buffer
+  int nraw_log2;        // log2 of the number of staged-input buffers (2, 4 or 8)
   int checked;          // the convolution has padding: bounds test per gathered element
   int vec;              // gout rows can be read with 128-bit loads
   long long* dbg;       // optional per-role cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
+  int skip;             // experiments (knob convtc_debug >> 1): bit 0 = gather warps skip their loads / TMEM stores, bit 1 = loaders skip split / stores
 };
 
 constexpr int kWgAStages = 6;
@@ -580,17 +582,21 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
   const uint32_t stage_bytes = 2u * b_bytes;
   const int SB = a.SB;
   const uint32_t raw_base = smem_base + (uint32_t)SB * stage_bytes;
-  const uint32_t bar_base = raw_base + 2u * a.raw_bytes;
+  // staged-input ring: an image is only `spi` stages (~0.5 us of MMAs) of work but its bulk copy takes ~1.5 us to land: with
+  // two buffers (one image of prefetch) the whole kernel ran at the latency of one bulk copy per image — 170 us with the
+  // gather and loader work switched off (profiles/r02_conv_tc_issue_analysis.md).  Up to 8 buffers = 7 images ahead.
+  const int NRAW = 1 << a.nraw_log2;
+  const uint32_t bar_base = raw_base + (uint32_t)NRAW * a.raw_bytes;
   auto full_a = [&](int s) { return bar_base + 8u * s; };               // 6
   auto empty_a = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
   auto full_b = [&](int s) { return bar_base + 8u * (12 + s); };        // 8
   auto empty_b = [&](int s) { return bar_base + 8u * (20 + s); };       // 8
   auto tfull_bar = [&](int b) { return bar_base + 8u * (28 + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (30 + b); };
-  auto raw_full = [&](int b) { return bar_base + 8u * (32 + b); };
-  auto raw_empty = [&](int b) { return bar_base + 8u * (34 + b); };
+  auto raw_full = [&](int b) { return bar_base + 8u * (40 + b); };       // 8
+  auto raw_empty = [&](int b) { return bar_base + 8u * (48 + b); };      // 8
   const uint32_t tmem_slot = bar_base + 8u * 36;
-  const uint32_t ptab = bar_base + 8u * 38;                               // int2 per output pixel: {byte offset of (h0, w0), h0 | w0 << 16}
+  const uint32_t ptab = bar_base + 8u * 56;                               // int2 per output pixel: {byte offset of (h0, w0), h0 | w0 << 16}
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = ptx::lane_id();
@@ -613,10 +619,8 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kWgAStages; s++) { ptx::mbar_init(full_a(s), 128); ptx::mbar_init(empty_a(s), 1); }
     for (int s = 0; s < SB; s++) { ptx::mbar_init(full_b(s), 128); ptx::mbar_init(empty_b(s), 1); }
-    for (int b = 0; b < 2; b++) {
-      ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4);
-      ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G);
-    }
+    for (int b = 0; b < 2; b++) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < NRAW; b++) { ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
@@ -635,8 +639,8 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       if (ptx::elect_one()) {
         const uint32_t bytes = (uint32_t)(nci * HWi) * 4u;
         for (int64_t i = 0; i < nimg; i++) {
-          const int b = (int)(i & 1);
-          ptx::mbar_wait(raw_empty(b), (uint32_t)((i >> 1) & 1) ^ 1u);
+          const int b = (int)(i & (NRAW - 1));
+          ptx::mbar_wait(raw_empty(b), (uint32_t)((i >> a.nraw_log2) & 1) ^ 1u);
           const int64_t n = slice + i * a.nslices;
           ptx::mbar_arrive_expect_tx(raw_full(b), bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -708,8 +712,8 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     // stage counters advance by compare-and-wrap (no 64-bit `it % G`, `it % stages`, `it / stages` per stage and thread)
     int turn = 0, sa_run = 0; uint32_t pa_run = 1u;              // whose stage this is | ring position | wait parity of the ring lap
     for (int64_t i = 0; i < nimg; i++) {
-      const int b = (int)(i & 1);
-      WG_TWAIT(w_rf, raw_full(b), (uint32_t)((i >> 1) & 1));      // every group waits for every image (keeps the phases of raw_empty in step)
+      const int b = (int)(i & (NRAW - 1));
+      WG_TWAIT(w_rf, raw_full(b), (uint32_t)((i >> a.nraw_log2) & 1));      // every group waits for every image (keeps the phases of raw_empty in step)
       const uint32_t xb = raw_base + (uint32_t)b * a.raw_bytes + (uint32_t)(base * 4);
       for (int s = 0; s < a.spi; s++) {
         const int sa = sa_run; const uint32_t pa = pa_run;
@@ -723,6 +727,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
         const int q0 = s * 32;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
+          if (a.skip & 1) break;
           float v[16];
           if (kind == 1) {
 #pragma unroll
@@ -801,9 +806,25 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
     // a stage is consumed in ~500 cycles (12 MMAs) but one L2 round trip takes longer: the loads of stage it + 2 are issued
     // before stage it is split and stored (three register buffers, rotated by a 3x unrolled loop — no register copies).
     // With a distance of one stage the MMA thread spent 37 % of its time waiting for grad_output (r02_convtc_waits.txt).
+    // Fast path (128-bit aligned rows, every stage full: HWo % 32 == 0): straight-line loads through a running pointer.  The
+    // generic fetch above costs ~250 instructions of branches and a division per stage and made the 4 loader warps — which
+    // run every stage one after the other — the slowest role of the kernel (the MMA thread waited 60 % of its time for
+    // grad_output stages even with the split and the stores switched off, profiles/r02_conv_tc_issue_analysis.md).
+    const bool fast = a.vec && (HWo % 32 == 0);
+    const float* run_src = a.gout + ((int64_t)slice * a.CO + co) * (int64_t)HWo + part * ppt;
+    const int64_t img_step = (int64_t)a.nslices * a.CO * HWo - (int64_t)(a.spi - 1) * 32;
+    int run_s = 0;
+    const bool row_ok = co < a.CO;
+    auto fetch_seq = [&](int64_t it, float4 (&dst)[4]) {            // called with it = 0, 1, 2, ... in order
+      if (!fast) { fetch(it, dst); return; }
+#pragma unroll
+      for (int v4 = 0; v4 < 4; v4++)
+        dst[v4] = (row_ok && v4 < nv) ? __ldg(reinterpret_cast<const float4*>(run_src) + v4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (++run_s == a.spi) { run_s = 0; run_src += img_step; } else run_src += 32;
+    };
     float4 bufA[4], bufB[4], bufC[4];
-    if (T > 0) fetch(0, bufA);
-    if (T > 1) fetch(1, bufB);
+    if (T > 0) fetch_seq(0, bufA);
+    if (T > 1) fetch_seq(1, bufB);
     long long w_eb = 0;
     const long long tstart = pclk();
     int sbi = 0; uint32_t pb = 1u;
@@ -812,7 +833,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
 #pragma unroll
       for (int v4 = 0; v4 < 4; v4++) {
-        if (v4 < nv) {
+        if (v4 < nv && !(a.skip & 2)) {
           const float v[4] = {cur[v4].x, cur[v4].y, cur[v4].z, cur[v4].w};
           float h4[4], l4[4];
 #pragma unroll
@@ -827,19 +848,19 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + b_bytes + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (!(a.skip & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b(sbi)) : "memory");
       if (++sbi == SB) { sbi = 0; pb ^= 1u; }
     };
     for (int64_t it = 0; it < T; it += 3) {
-      if (it + 2 < T) fetch(it + 2, bufC);
+      if (it + 2 < T) fetch_seq(it + 2, bufC);
       consume(bufA);
       if (it + 1 < T) {
-        if (it + 3 < T) fetch(it + 3, bufA);
+        if (it + 3 < T) fetch_seq(it + 3, bufA);
         consume(bufB);
       }
       if (it + 2 < T) {
-        if (it + 4 < T) fetch(it + 4, bufB);
+        if (it + 4 < T) fetch_seq(it + 4, bufB);
         consume(bufC);
       }
     }
@@ -931,7 +952,10 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
   const int nci_max = 127 / KK + 2 < a.C ? 127 / KK + 2 : a.C;
   a.raw_bytes = (uint32_t)round_up((int64_t)nci_max * HWi * 4, 128);
   const size_t stage_bytes = 2 * (size_t)a.NP * 128;
-  const size_t fixed = 1024 + 2 * (size_t)a.raw_bytes + 8 * 38 + (size_t)a.spi * 32 * 8 + 64;
+  a.nraw_log2 = 1;
+  for (int lg = 3; lg >= 2; lg--)       // as many staged-input buffers as leave room for a grad_output ring of 6 stages
+    if (1024 + ((size_t)a.raw_bytes << lg) + 8 * 56 + (size_t)a.spi * 32 * 8 + 64 + 6 * stage_bytes <= 227 * 1024) { a.nraw_log2 = lg; break; }
+  const size_t fixed = 1024 + ((size_t)a.raw_bytes << a.nraw_log2) + 8 * 56 + (size_t)a.spi * 32 * 8 + 64;
   if (fixed + 2 * stage_bytes > 227 * 1024) return AM_OK;
   int SB = (int)((227 * 1024 - fixed) / stage_bytes);
   if (SB > 8) SB = 8;
@@ -942,8 +966,9 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
   a.part = (float*)part;
   const size_t smem = fixed + (size_t)SB * stage_bytes;
   AM_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.skip = tuning(kTuneConvTcDebug) >> 1;
   int dbg_env;
-  dbg_env = tuning(kTuneConvTcDebug) ? 1 : 0;
+  dbg_env = tuning(kTuneConvTcDebug) & 1;
   a.dbg = nullptr;
   if (dbg_env) {
     void* base = nullptr;

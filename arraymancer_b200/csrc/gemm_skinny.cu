@@ -135,26 +135,42 @@ __global__ void __launch_bounds__(256) skinny_nk_kernel(const SkinnyArgs<T> a) {
   bool rok[R];
 #pragma unroll
   for (int r = 0; r < R; r++) { rok[r] = g0 + r < a.Gd; rowp[r] = a.big + (rok[r] ? (g0 + r) : 0) * a.bg_g; }
+  // the large operand of chunk c + 1 is requested before chunk c is multiplied: the loads' DRAM latency hides behind
+  // S * R * V * 2 FMAs per lane instead of being paid after every barrier (first version: 0.27 of the HBM roof at N = 16)
+  union VB { Vec q; T e[V]; };
+  VB nxt[2][R];
+  auto load_big = [&](int64_t kc, VB (&dst)[2][R]) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int64_t k = kc + (j * 32 + lane) * V;        // K % V == 0 and split slices are multiples of KC: k + V <= ke or k >= ke
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (rok[r] && k < ke) dst[j][r].q = __ldg(reinterpret_cast<const Vec*>(rowp[r] + k));
+        else {
+#pragma unroll
+          for (int v = 0; v < V; v++) dst[j][r].e[v] = T(0);
+        }
+      }
+    }
+  };
+  constexpr bool PF = sizeof(T) == 4;                 // 8-byte types: the accumulators alone take 128 registers, no room to prefetch
+  if (PF && kb < ke) load_big(kb, nxt);
   for (int64_t kc = kb; kc < ke; kc += KC) {
     __syncthreads();
     for (int i = tid; i < S * KC; i += 256) {
       const int s = i / KC, k = i - s * KC;
       ths[s][k] = (s < a.S && kc + k < ke) ? a.thin[s * a.th_s + (kc + k) * a.th_k] : T(0);
     }
-    __syncthreads();
-    union { Vec q; T e[V]; } vb[2][R];
+    VB vb[2][R];
+    if constexpr (PF) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int64_t k = kc + (j * 32 + lane) * V;        // K % V == 0 and split slices are multiples of KC: k + V <= ke or k >= ke
+      for (int j = 0; j < 2; j++)
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (rok[r] && k < ke) vb[j][r].q = __ldg(reinterpret_cast<const Vec*>(rowp[r] + k));
-        else {
-#pragma unroll
-          for (int v = 0; v < V; v++) vb[j][r].e[v] = T(0);
-        }
-      }
+        for (int r = 0; r < R; r++) vb[j][r].q = nxt[j][r].q;
+      if (kc + KC < ke) load_big(kc + KC, nxt);
     }
+    __syncthreads();
+    if constexpr (!PF) load_big(kc, vb);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll

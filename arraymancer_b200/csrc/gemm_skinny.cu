@@ -238,6 +238,16 @@ static int launch_skinny(cudaStream_t st, SkinnyArgs<T> a, bool kn, int splits) 
   return AM_OK;
 }
 
+// resident CTAs of the chosen kernel on the whole chip (sizes the split-K grid, see gemm_skinny)
+template <class T, int S>
+static int64_t skinny_slots(bool kn) {
+  int per_sm = 0;
+  cudaError_t e = kn ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, skinny_kn_kernel<T, S>, 128, 0)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, skinny_nk_kernel<T, S>, 256, 0);
+  if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  return (int64_t)per_sm * sm_count();
+}
+
 // *done = false: the shape / layout is not a skinny case this file handles (caller continues with the general kernel).
 template <class T>
 int gemm_skinny(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t rsA, int64_t csA, const T* B,
@@ -261,13 +271,28 @@ int gemm_skinny(cudaStream_t st, int64_t M, int64_t N, int64_t K, T alpha, const
   // split K so that the grid holds ~4 CTAs per SM; slices are multiples of the k-chunk of the kernel
   const int64_t KC = kn ? 128 : 32 * V * 2;
   const int64_t ctas_g = kn ? ceil_div(a.Gd, 128 * V) : ceil_div(a.Gd, 32);
-  int64_t splits = ceil_div(4 * (int64_t)sm_count(), ctas_g);
+  const int SP = a.S <= 1 ? 1 : a.S <= 2 ? 2 : a.S <= 4 ? 4 : a.S <= 8 ? 8 : 16;
+  int64_t slots;
+  switch (SP) {
+    case 1: slots = skinny_slots<T, 1>(kn); break;
+    case 2: slots = skinny_slots<T, 2>(kn); break;
+    case 4: slots = skinny_slots<T, 4>(kn); break;
+    case 8: slots = skinny_slots<T, 8>(kn); break;
+    default: slots = skinny_slots<T, 16>(kn); break;
+  }
+  // split-K depth, measured at 16384^2 (profiles/r02 bench, GB/s of the large operand): what matters is the number of loads in
+  // flight, so the thin kernels (S = 1: few registers, up to 16 CTAs per SM) fill every resident slot — M = 1: 3.0 -> 4.6 TB/s,
+  // N = 1: 5.9 -> 6.2 TB/s with one full wave — while the register-heavy S > 1 kernels keep the ~4 CTAs per SM of round 1
+  // (one exact wave of fewer CTAs measured 12 % slower there).
+  const int64_t per_sm = slots / sm_count();
+  int64_t splits;
+  if (SP == 1 && !kn) splits = slots / ctas_g;
+  else splits = ceil_div((SP == 1 && per_sm > 4 ? per_sm : 4) * (int64_t)sm_count(), ctas_g);
   const int64_t max_splits = ceil_div(K, 4 * KC);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.k_per_split = round_up(ceil_div(K, splits), KC);
-  splits = ceil_div(K, a.k_per_split);
-  const int SP = a.S <= 1 ? 1 : a.S <= 2 ? 2 : a.S <= 4 ? 4 : a.S <= 8 ? 8 : 16;
+  splits = ceil_div(K, a.k_per_split);                 // (rounding the slice up can only lower the count)
   a.part = nullptr;
   if (splits > 1) {
     void* p = nullptr;

@@ -52,7 +52,7 @@ if what in ("conv", "convtc", "all"):
         torch.cuda.synchronize()
 if what == "skinny":
     n = 16384
-    for shape in ((16, n, n), (n, 16, n)):
+    for shape in ((1, n, n), (n, 1, n), (16, n, n), (n, 16, n)):
         M, N, K = shape
         A = torch.rand(M, K, device="cuda") * 2 - 1; B = torch.rand(K, N, device="cuda") * 2 - 1
         C = torch.empty(M, N, device="cuda")

@@ -230,3 +230,42 @@ def test_lenet_step_resident(am):
         # argmax / relu masks can flip on near-ties between the GPU and CPU pipelines; at batch 16 with these inputs they
         # do not, and the gradients agree to the backward tolerance
         assert rel(got.cpu().numpy().reshape(np.asarray(want).shape), want) <= 2e-4, name
+
+
+def test_conv_and_companions_are_cuda_graph_capturable(am):
+    """The device entries only enqueue on the given stream (include/am_b200.h, 'CUDA graphs'): after one eager call has
+    sized the scratch buffers, a conv forward + backward (both LeNet layers: cv1 kernels and the tcgen05 kernels) plus
+    relu / maxpool can be stream-captured and replayed with identical bits."""
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    layers = []
+    for xs, ks in (((64, 1, 28, 28), (20, 1, 5, 5)), ((64, 20, 12, 12), (50, 20, 5, 5))):
+        X = torch.rand(xs, device="cuda", generator=g); W = torch.randn(ks, device="cuda", generator=g) * 0.1
+        B = torch.rand((ks[0], 1, 1), device="cuda", generator=g)
+        G = torch.rand((xs[0], ks[0], xs[2] - 4, xs[3] - 4), device="cuda", generator=g) - 0.5
+        layers.append((X, W, B, G))
+
+    def body():
+        outs = []
+        for X, W, B, G in layers:
+            y = am.conv2d(X, W, B)
+            r = am.relu(y)
+            idx, p = am.maxpool2d(r, (2, 2), (0, 0), (2, 2))
+            gi, gw, gb = am.conv2d_backward(X, W, B, (0, 0), (1, 1), (1, 1), G)
+            outs += [y, r, p, gi, gw, gb]
+        return outs
+    eager = [t.clone() for t in body()]                     # also sizes every workspace
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+        captured = body()
+    for t in captured:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for a_, b_ in zip(captured, eager):
+        assert torch.equal(a_, b_)
+    # and the eager path still works afterwards, on the default stream
+    again = body()
+    torch.cuda.synchronize()
+    for a_, b_ in zip(again, eager):
+        assert torch.equal(a_, b_)

@@ -49,6 +49,22 @@ __global__ void __launch_bounds__(128) skinny_kn_kernel(const SkinnyArgs<T> a) {
 #pragma unroll
     for (int v = 0; v < V; v++) acc[s][v] = T(0);
   const T* bp = a.big + g0;
+  // the U loads of the NEXT group of k steps are issued before the current group is multiplied — also across the barriers
+  // of the thin-operand staging, so the DRAM stream never drains at a chunk boundary
+  union VB { Vec q; T e[V]; };
+  VB nxt[U];
+  auto load_grp = [&](int64_t k0, VB (&dst)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (g_ok && k0 + u < ke) dst[u].q = __ldg(reinterpret_cast<const Vec*>(bp + (k0 + u) * a.bg_k));
+      else {
+#pragma unroll
+        for (int v = 0; v < V; v++) dst[u].e[v] = T(0);
+      }
+    }
+  };
+  constexpr bool PF = S <= 4;                          // S = 8 / 16: the second buffer costs occupancy (measured: 0.62 -> 0.48)
+  if (PF) load_grp(kb, nxt);
   for (int64_t kc = kb; kc < ke; kc += KC) {
     __syncthreads();
     for (int i = tid; i < KC * S; i += 128) {
@@ -56,16 +72,22 @@ __global__ void __launch_bounds__(128) skinny_kn_kernel(const SkinnyArgs<T> a) {
       ths[k][s] = (s < a.S && kc + k < ke) ? a.thin[s * a.th_s + (kc + k) * a.th_k] : T(0);
     }
     __syncthreads();
-    if (!g_ok) continue;
+    if (!PF && !g_ok) continue;
     const int kn = (int)((ke - kc < KC) ? ke - kc : KC);
     for (int k = 0; k < kn; k += U) {
-      union { Vec q; T e[V]; } vb[U];
+      VB vb[U];
+      if constexpr (PF) {
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (k + u < kn) vb[u].q = __ldg(reinterpret_cast<const Vec*>(bp + (kc + k + u) * a.bg_k));
-        else {
+        for (int u = 0; u < U; u++) vb[u].q = nxt[u].q;
+        load_grp(kc + k + U, nxt);                         // k steps past ke load nothing (zeros)
+      } else {
 #pragma unroll
-          for (int v = 0; v < V; v++) vb[u].e[v] = T(0);
+        for (int u = 0; u < U; u++) {
+          if (k + u < kn) vb[u].q = __ldg(reinterpret_cast<const Vec*>(bp + (kc + k + u) * a.bg_k));
+          else {
+#pragma unroll
+            for (int v = 0; v < V; v++) vb[u].e[v] = T(0);
+          }
         }
       }
 #pragma unroll

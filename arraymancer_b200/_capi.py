@@ -20,7 +20,7 @@ SUFFIXES = ("f32", "f64", "i32", "i64")
 CTYPE = {"f32": ctypes.c_float, "f64": ctypes.c_double, "i32": ctypes.c_int32, "i64": ctypes.c_int64}
 
 # every symbol include/am_b200.h declares (tests check the library exports all of them)
-NN_OPS = ("relu_forward", "relu_backward", "maxpool2d_forward", "maxpool2d_backward", "linear_forward", "linear_backward",
+NN_OPS = ("relu_forward", "relu_backward", "maxpool2d_forward", "maxpool2d_backward", "maxpool2d_backward_relu", "linear_forward", "linear_backward",
           "sparse_softmax_cross_entropy", "sparse_softmax_cross_entropy_backward")
 EXPORTED_SYMBOLS = (
     ["am_version", "am_last_error", "am_device_info", "am_shutdown", "am_set_f32_path", "am_get_f32_path", "am_set_f64_path", "am_get_f64_path", "am_set_conv_path",
@@ -120,6 +120,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"am_relu_backward_{s}").argtypes = [p, i64, p, p, p]
         getattr(L, f"am_maxpool2d_forward_{s}").argtypes = [p] + [i64] * 10 + [p, p, p]
         getattr(L, f"am_maxpool2d_backward_{s}").argtypes = [p, i64, i64, p, p, p, ci]
+        getattr(L, f"am_maxpool2d_backward_relu_{s}").argtypes = [p, i64, i64, p, p, p, p, ci]
         getattr(L, f"am_linear_forward_{s}").argtypes = [p, i64, i64, i64, p, p, p, p]
         getattr(L, f"am_linear_backward_{s}").argtypes = [p, i64, i64, i64, p, p, p, p, p, p]
         getattr(L, f"am_sparse_softmax_cross_entropy_{s}").argtypes = [p, i64, i64, p, i64, i64, p, p]

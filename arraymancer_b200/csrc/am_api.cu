@@ -571,7 +571,12 @@ DEF_CONV(i64, int64_t)
   }                                                                                                            \
   int am_maxpool2d_backward_##SUF(am_stream_t s, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, T* gi, \
                                   int overlap) {                                                               \
-    return maxpool2d_backward<T>((cudaStream_t)s, n_in, n_out, idx, go, gi, overlap);                          \
+    return maxpool2d_backward<T>((cudaStream_t)s, n_in, n_out, idx, go, nullptr, gi, overlap);                 \
+  }                                                                                                            \
+  int am_maxpool2d_backward_relu_##SUF(am_stream_t s, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, \
+                                       const T* relu_cached, T* gi, int overlap) {                             \
+    if (n_in > 0 && !relu_cached) { set_last_error("maxpool2d_backward_relu: null cached tensor"); return AM_ERR_INVALID; } \
+    return maxpool2d_backward<T>((cudaStream_t)s, n_in, n_out, idx, go, relu_cached, gi, overlap);             \
   }                                                                                                            \
   int am_linear_forward_##SUF(am_stream_t s, int64_t b, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y) { \
     return linear_forward<T>((cudaStream_t)s, b, in, out, x, w, bias, y);                                      \

@@ -90,7 +90,8 @@ template <class T>
 int maxpool2d_forward(cudaStream_t st, int64_t N, int64_t C, int64_t H, int64_t W, int64_t kH, int64_t kW, int64_t padH,
                       int64_t padW, int64_t sH, int64_t sW, const T* x, T* y, int64_t* idx);
 template <class T>
-int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, T* gi, int windows_overlap);
+int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, const T* relu_cached, T* gi,
+                       int windows_overlap);
 template <class T>
 int linear_forward(cudaStream_t st, int64_t batch, int64_t in, int64_t out, const T* x, const T* w, const T* bias, T* y);
 template <class T>

@@ -174,12 +174,19 @@ __global__ void maxpool_owner_kernel(const int64_t* __restrict__ idx, long long*
     if (j >= 0 && j < n_in) atomicMax(&owner[j], (long long)i);
   }
 }
+// relu_cached != null: the relu_backward of a conv -> relu -> maxpool block (nnp_activation.nim:65-70, `cached <= 0 ? 0 :
+// gradient`) is applied to the one element per window that receives a gradient — one gathered load per POOLED output
+// instead of an element-wise pass (read gradient, read cached, write) over the whole activation tensor.
 template <class T>
 __global__ void maxpool_bwd_kernel(const int64_t* __restrict__ idx, const long long* __restrict__ owner, const T* __restrict__ go,
-                                   T* __restrict__ gi, int64_t n_out, int64_t n_in) {
+                                   const T* __restrict__ relu_cached, T* __restrict__ gi, int64_t n_out, int64_t n_in) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = idx[i];
-    if (j >= 0 && j < n_in && (owner == nullptr || owner[j] == (long long)i)) gi[j] = go[i];
+    if (j >= 0 && j < n_in && (owner == nullptr || owner[j] == (long long)i)) {
+      T g = go[i];
+      if (relu_cached != nullptr && relu_cached[j] <= T(0)) g = T(0);
+      gi[j] = g;
+    }
   }
 }
 
@@ -211,7 +218,8 @@ int maxpool2d_forward(cudaStream_t st, int64_t N, int64_t C, int64_t H, int64_t 
 }
 
 template <class T>
-int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, T* gi, int windows_overlap) {
+int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64_t* idx, const T* go, const T* relu_cached, T* gi,
+                       int windows_overlap) {
   if (n_in < 0 || n_out < 0 || (n_in > 0 && !gi) || (n_out > 0 && (!idx || !go))) { set_last_error("maxpool2d_backward: bad argument"); return AM_ERR_INVALID; }
   if (n_in == 0) return AM_OK;
   AM_CUDA_TRY(cudaMemsetAsync(gi, 0, (size_t)n_in * sizeof(T), st));                      // zeros(cached_input_shape)
@@ -226,7 +234,7 @@ int maxpool2d_backward(cudaStream_t st, int64_t n_in, int64_t n_out, const int64
     maxpool_owner_kernel<<<grid_for(n_out, 256), 256, 0, st>>>(idx, owner, n_out, n_in);
     g_launch_count++;
   }
-  maxpool_bwd_kernel<T><<<grid_for(n_out, 256), 256, 0, st>>>(idx, owner, go, gi, n_out, n_in);
+  maxpool_bwd_kernel<T><<<grid_for(n_out, 256), 256, 0, st>>>(idx, owner, go, relu_cached, gi, n_out, n_in);
   g_launch_count++;
   AM_CUDA_TRY(cudaGetLastError());
   return AM_OK;
@@ -398,7 +406,7 @@ int ssce_backward(cudaStream_t st, int64_t batch, int64_t features, T grad, cons
   template int relu_backward<T>(cudaStream_t, int64_t, const T*, const T*, T*);                                          \
   template int maxpool2d_forward<T>(cudaStream_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, \
                                     int64_t, int64_t, const T*, T*, int64_t*);                                           \
-  template int maxpool2d_backward<T>(cudaStream_t, int64_t, int64_t, const int64_t*, const T*, T*, int);                 \
+  template int maxpool2d_backward<T>(cudaStream_t, int64_t, int64_t, const int64_t*, const T*, const T*, T*, int);       \
   template int linear_forward<T>(cudaStream_t, int64_t, int64_t, int64_t, const T*, const T*, const T*, T*);             \
   template int linear_backward<T>(cudaStream_t, int64_t, int64_t, int64_t, const T*, const T*, const T*, T*, T*, T*);
 INST(float)

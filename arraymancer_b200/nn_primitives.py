@@ -195,20 +195,31 @@ def maxpool2d(input: torch.Tensor, kernel, padding=(0, 0), stride=(1, 1)):
 
 
 def maxpool2d_backward(cached_input_shape, cached_max_indices: torch.Tensor, grad_output: torch.Tensor,
-                       windows_overlap: bool = True) -> torch.Tensor:
+                       windows_overlap: bool = True, relu_cached: torch.Tensor | None = None) -> torch.Tensor:
     """gradInput = zeros; gradInput[max_indices[i]] = gradOutput[i] (nnp_maxpooling.nim:68-83).  Pass
     windows_overlap=False when stride >= kernel (every input belongs to one window): skips the pass that
-    reproduces the serial reference's "last writer wins"."""
+    reproduces the serial reference's "last writer wins".
+    relu_cached (the tensor the pooled layer's input was relu'd from / to, same shape as the result): additionally applies
+    relu_backward (nnp_activation.nim:65-70) in the same pass — identical bits to the two separate calls."""
     suf = _fcheck("maxpool2d_backward", grad_output)
     if cached_max_indices.dtype != torch.int64 or not cached_max_indices.is_cuda or not cached_max_indices.is_contiguous():
         raise TypeError("maxpool2d_backward: max_indices must be a contiguous int64 GPU tensor")
     if cached_max_indices.numel() != grad_output.numel():
         raise IndexError("maxpool2d_backward: gradOutput and max_indices sizes differ")
     gin = torch.empty(tuple(cached_input_shape), dtype=grad_output.dtype, device=grad_output.device)
+    if relu_cached is not None:
+        if (relu_cached.dtype != grad_output.dtype or tuple(relu_cached.shape) != tuple(cached_input_shape)
+                or not relu_cached.is_cuda or not relu_cached.is_contiguous()):
+            raise ValueError("maxpool2d_backward: relu_cached must be a contiguous GPU tensor of the input's shape and dtype")
     with torch.cuda.device(grad_output.device):
-        _capi.check(getattr(_capi.lib(), f"am_maxpool2d_backward_{suf}")(
-            _stream_ptr(grad_output), gin.numel(), grad_output.numel(), cached_max_indices.data_ptr(),
-            grad_output.data_ptr(), gin.data_ptr(), 1 if windows_overlap else 0))
+        if relu_cached is None:
+            _capi.check(getattr(_capi.lib(), f"am_maxpool2d_backward_{suf}")(
+                _stream_ptr(grad_output), gin.numel(), grad_output.numel(), cached_max_indices.data_ptr(),
+                grad_output.data_ptr(), gin.data_ptr(), 1 if windows_overlap else 0))
+        else:
+            _capi.check(getattr(_capi.lib(), f"am_maxpool2d_backward_relu_{suf}")(
+                _stream_ptr(grad_output), gin.numel(), grad_output.numel(), cached_max_indices.data_ptr(),
+                grad_output.data_ptr(), relu_cached.data_ptr(), gin.data_ptr(), 1 if windows_overlap else 0))
     return gin
 
 

@@ -317,6 +317,10 @@ AM_API int am_mg_host_gemm_f32(am_mg_ctx* ctx, int64_t M, int64_t N, int64_t K, 
  *                                    first maximum wins; backward ASSIGNS grad_out[i] to grad_in[max_indices[i]],
  *                                    the last i wins where windows overlap: pass windows_overlap = 1 unless
  *                                    stride >= kernel in both dimensions)
+ *   maxpool2d_backward_relu          = relu_backward(maxpool2d_backward(grad_out), relu_cached), bit for bit, in ONE pass:
+ *                                    the mask of nnp_activation.nim:65-70 is applied to the one element per window that
+ *                                    receives a gradient (conv -> relu -> maxpool blocks of ex02_mnist.nim: the
+ *                                    element-wise relu_backward pass over the conv output disappears)
  *   linear / linear_backward         nn_primitives/nnp_linear.nim:20-66  (y = x*W^T + b; gI = gO*W, gW = gO^T*x,
  *                                    gB = sum(gO, axis 0); bias / any gradient pointer may be NULL)
  *   sparse_softmax_cross_entropy     nn_primitives/nnp_softmax_cross_entropy.nim:100-178 (mean over the batch of
@@ -331,6 +335,9 @@ AM_API int am_mg_host_gemm_f32(am_mg_ctx* ctx, int64_t M, int64_t N, int64_t K, 
   AM_API int am_maxpool2d_backward_##SUF(am_stream_t stream, int64_t n_input, int64_t n_output,              \
                                          const int64_t* max_indices, const T* grad_output, T* grad_input,    \
                                          int windows_overlap);                                               \
+  AM_API int am_maxpool2d_backward_relu_##SUF(am_stream_t stream, int64_t n_input, int64_t n_output,         \
+                                              const int64_t* max_indices, const T* grad_output,              \
+                                              const T* relu_cached, T* grad_input, int windows_overlap);     \
   AM_API int am_linear_forward_##SUF(am_stream_t stream, int64_t batch, int64_t in_features, int64_t out_features, \
                                      const T* input, const T* weight, const T* bias, T* output);             \
   AM_API int am_linear_backward_##SUF(am_stream_t stream, int64_t batch, int64_t in_features, int64_t out_features, \

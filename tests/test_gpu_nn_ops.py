@@ -83,6 +83,17 @@ def test_maxpool_vs_oracle(am, dt, ci):
     if stride[0] >= kernel[0] and stride[1] >= kernel[1]:
         got2 = am.maxpool2d_backward(shape, idx, dev(go), windows_overlap=False).cpu().numpy()
         assert np.array_equal(got2, want)
+    # fused relu_backward (am_maxpool2d_backward_relu_*): identical bits to relu_backward(maxpool2d_backward(go), cached), and
+    # to the oracle's composition (nnp_maxpooling.nim:68-83 then nnp_activation.nim:65-70); cached holds zeros, negatives, NaN
+    cached = x.copy()
+    cached[(rng.random(shape) < 0.1)] = np.nan
+    want_f = O.relu_backward(want, cached)
+    sep = am.relu_backward(am.maxpool2d_backward(shape, idx, dev(go)), dev(cached)).cpu().numpy()
+    fused = am.maxpool2d_backward(shape, idx, dev(go), relu_cached=dev(cached)).cpu().numpy()
+    assert np.array_equal(sep, want_f) and np.array_equal(fused, want_f)
+    if stride[0] >= kernel[0] and stride[1] >= kernel[1]:
+        fused2 = am.maxpool2d_backward(shape, idx, dev(go), windows_overlap=False, relu_cached=dev(cached)).cpu().numpy()
+        assert np.array_equal(fused2, want_f)
 
 
 @pytest.mark.parametrize("dt", ["f32", "f64"])
@@ -218,9 +229,11 @@ def test_lenet_step_resident(am):
     GRH, GW4, GB4 = am.linear_backward(RH, W4, GL)
     GH = am.relu_backward(GRH, H)
     GF, GW3, GB3 = am.linear_backward(F, W3, GH)
-    GR2 = am.maxpool2d_backward(R2.shape, I2, GF.reshape(P2.shape), windows_overlap=False); GC2 = am.relu_backward(GR2, C2)
+    # pooling backward with the relu mask fused (one pass instead of maxpool2d_backward + relu_backward)
+    GC2 = am.maxpool2d_backward(R2.shape, I2, GF.reshape(P2.shape), windows_overlap=False, relu_cached=C2)
+    assert torch.equal(GC2, am.relu_backward(am.maxpool2d_backward(R2.shape, I2, GF.reshape(P2.shape), windows_overlap=False), C2))
     GP1, GW2, GB2 = am.conv2d_backward(P1, W2, B2, (0, 0), (1, 1), (1, 1), GC2)
-    GR1 = am.maxpool2d_backward(R1.shape, I1, GP1, windows_overlap=False); GC1 = am.relu_backward(GR1, C1)
+    GC1 = am.maxpool2d_backward(R1.shape, I1, GP1, windows_overlap=False, relu_cached=C1)
     GX, GW1, GB1 = am.conv2d_backward(X, W1, B1, (0, 0), (1, 1), (1, 1), GC1)
 
     assert abs(dloss - loss) <= 2e-5 * max(1.0, abs(loss))

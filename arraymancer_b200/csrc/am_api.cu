@@ -81,9 +81,9 @@ static std::atomic<int> g_f32_path{AM_F32_AUTO};
 static std::atomic<int> g_f64_path{AM_F64_AUTO};
 
 // ------------------------------------------------------------------ explicit tuning knobs (no environment variables)
-static std::atomic<int> g_tune[kTuneCount] = {{2}, {8}, {1}, {0}, {0}, {0}, {0}, {0}, {1}, {1}, {1}, {4}};
+static std::atomic<int> g_tune[kTuneCount] = {{2}, {8}, {1}, {0}, {0}, {0}, {0}, {0}, {1}, {1}, {1}, {4}, {1}};
 static const char* const kTuneNames[kTuneCount] = {"tc_flush_kb", "tc_group", "tc_sync", "pack_scalar", "host_rowchunks",
-                                                   "convtc_groups", "convtc_debug", "convtc_dgrad_gather", "simt_vec_load", "dmma_tma", "convtc_hi_resident", "convtc_flush_kb"};
+                                                   "convtc_groups", "convtc_debug", "convtc_dgrad_gather", "simt_vec_load", "dmma_tma", "convtc_hi_resident", "convtc_flush_kb", "convtc_wgrad_tma"};
 int tuning(int key) { return (key >= 0 && key < kTuneCount) ? g_tune[key].load(std::memory_order_relaxed) : 0; }
 static int tune_key(const char* name) {
   if (!name) return -1;

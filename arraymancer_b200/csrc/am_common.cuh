@@ -21,7 +21,8 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns AM_ERR_CU
 // ---- per-device workspace cache (the shim may keep one, freed by am_shutdown) --
 // slot ids
 enum WsSlot : int { kWsSplitA = 0, kWsSplitB = 1, kWsConv = 2, kWsConvTab = 3, kWsMisc = 4, kWsConvW = 5, kWsNn = 6,
-                    kWsStrideIn = 7, kWsStrideK = 8, kWsStrideGo = 9, kWsStrideOut = 10, kWsStrideGk = 11, kWsSkinny = 12, kWsNumSlots = 16 };
+                    kWsStrideIn = 7, kWsStrideK = 8, kWsStrideGo = 9, kWsStrideOut = 10, kWsStrideGk = 11, kWsSkinny = 12, kWsGoutSplit = 13,
+                    kWsNumSlots = 16 };
 // returns device pointer valid until the next workspace() call for the same (device,slot) with a larger size
 int workspace(int slot, size_t bytes, void** out);
 void workspace_release_all();

@@ -48,6 +48,14 @@ __device__ __forceinline__ long long pclk() {
 #endif
 
 
+// grad_output as pre-split tf32 hi / lo planes ([N][CO][HO*WO] each, lo right behind hi) for the TMA-fed weight-gradient
+// kernel: can they be used for this call?  (rows of 16-byte multiples, aligned base, at most 1 GiB of planes, knob on)
+static bool gout_planes_ok(const am_conv2d_desc& d, int64_t HWo, const float* grad_output, int64_t* total) {
+  *total = d.N * d.Cout * HWo;
+  return tuning(kTuneConvTcWgradTma) != 0 && HWo % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_output) & 15) == 0 &&
+         d.N < (1ll << 31) && *total > 0 && *total <= (1ll << 27);
+}
+
 struct DgradTcArgs {
   const float* gout;    // [N][CO][HO][WO]
   float* gin;           // [N][C][H][W]
@@ -217,6 +225,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_con
             for (int j = 0; j < 16; j++) ptx::split_tf32(v[c0 + j], hi[j], lo[j]);
             ptx::tmem_st_32x16(ta + (uint32_t)c0, hi);
             ptx::tmem_st_32x16(ta + (uint32_t)a.Kpad + (uint32_t)c0, lo);
+
           }
         }
         ptx::tmem_st_wait();
@@ -569,13 +578,38 @@ struct WgradTcArgs {
   int vec;              // gout rows can be read with 128-bit loads
   long long* dbg;       // optional per-role cycle counters of CTA 0 (AM_CONVTC_DEBUG=1)
   int skip;             // experiments (knob convtc_debug >> 1): bit 0 = gather warps skip their loads / TMEM stores, bit 1 = loaders skip split / stores
+  int b_tma;            // grad_output stages arrive by TMA from pre-split hi / lo planes (no loader warps)
 };
 
 constexpr int kWgAStages = 6;
+
+int make_tmap_f32_nd_sw128(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box);     // gemm_f32_tc.cu
+
+// grad_output -> tf32 hi / lo planes, once per call (storing them from the data-gradient kernel, which splits every element
+// for its own A operand, was measured: 100 extra stores per thread and tile on its operand warps cost 150 us, this pass 25): the 4 chunk CTAs of a batch slice then fetch their stages by TMA instead
+// of each splitting the same block with its loader warps (which were the slowest role of the kernel)
+__global__ void __launch_bounds__(256) wgrad_split_gout_kernel(const float4* __restrict__ g, float4* __restrict__ hi,
+                                                              float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g + i);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      uint32_t hb, lb;
+      ptx::split_tf32(x[e], hb, lb);
+      h[e] = __uint_as_float(hb); l[e] = __uint_as_float(lb);
+    }
+    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+    lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
 #define WG_TWAIT(counter, bar, ph) do { const long long t0_ = pclk(); ptx::mbar_wait(bar, ph); counter += pclk() - t0_; } while (0)
 
 
-__global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs a) {
+__global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGhi,
+                                                               const __grid_constant__ CUtensorMap tmGlo, const WgradTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)a.NP * 128u;                     // one plane of a gout stage: NP rows x 32 pixels
@@ -618,7 +652,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
 
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kWgAStages; s++) { ptx::mbar_init(full_a(s), 128); ptx::mbar_init(empty_a(s), 1); }
-    for (int s = 0; s < SB; s++) { ptx::mbar_init(full_b(s), 128); ptx::mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < SB; s++) { ptx::mbar_init(full_b(s), a.b_tma ? 1 : 128); ptx::mbar_init(empty_b(s), 1); }
     for (int b = 0; b < 2; b++) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4); }
     for (int b = 0; b < NRAW; b++) { ptx::mbar_init(raw_full(b), 1); ptx::mbar_init(raw_empty(b), 128u * (uint32_t)G); }
     ptx::fence_barrier_init();
@@ -690,6 +724,23 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
           if (++sbi == SB) { sbi = 0; pb ^= 1u; b0 = b_first; }
         }
         if (a.dbg && blockIdx.x == 0) { a.dbg[0] = pclk() - tstart; a.dbg[1] = w_te; a.dbg[2] = w_fa; a.dbg[3] = w_fb; }
+      }
+    } else if (warp == 2 && a.b_tma) {
+      // ===================== grad_output producer (TMA): [NP rows x 32 pixels] boxes of the pre-split hi / lo planes,
+      // 128-byte swizzled by the TMA unit; the four warps that used to load and split them are a fourth gather group
+      if (ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tmGhi); ptx::prefetch_tensormap(&tmGlo);
+        int sbi = 0; uint32_t pb = 1u;
+        int s_run = 0; int64_t n_run = slice;
+        for (int64_t it = 0; it < T; it++) {
+          ptx::mbar_wait(empty_b(sbi), pb);
+          const uint32_t sb = smem_base + (uint32_t)sbi * stage_bytes;
+          ptx::mbar_arrive_expect_tx(full_b(sbi), stage_bytes);
+          ptx::tma_load_3d(sb, &tmGhi, full_b(sbi), s_run * 32, 0, (int)n_run);
+          ptx::tma_load_3d(sb + b_bytes, &tmGlo, full_b(sbi), s_run * 32, 0, (int)n_run);
+          if (++s_run == a.spi) { s_run = 0; n_run += a.nslices; }
+          if (++sbi == SB) { sbi = 0; pb ^= 1u; }
+        }
       }
     }
   } else if (warp < 4 + 4 * G) {
@@ -767,11 +818,12 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(raw_empty(b)) : "memory");
     }
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[4] = pclk() - tstart; a.dbg[5] = w_rf; a.dbg[6] = w_ea; }
-  } else if (warp < 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // unused gather slots
+  } else if (warp < 16 || (a.b_tma && warp < 20)) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // unused gather slots (and the loader slot when TMA feeds B)
   } else if (warp < 20) {
     // ===================== loader warps: gout block [co x 32 pixels] -> tf32 hi/lo, K-major swizzled smem =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (!a.b_tma) {
     const int t = (int)threadIdx.x - 512;                       // 0..127
     const int tpr = 128 / a.NP;                                 // threads per row: 2, 4 or 8
     const int co = t / tpr, part = t - co * tpr;
@@ -865,6 +917,7 @@ __global__ void __launch_bounds__(768, 1) conv_wgrad_tc_kernel(const WgradTcArgs
       }
     }
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 512) { a.dbg[7] = pclk() - tstart; a.dbg[8] = w_eb; }
+    }
   } else {
     // ===================== accumulate warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
@@ -946,7 +999,7 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
   flush_env = tuning(kTuneTcFlushKb) > 0 ? tuning(kTuneTcFlushKb) : 2;
   groups_env = (tuning(kTuneConvTcGroups) >= 1 && tuning(kTuneConvTcGroups) <= 3) ? tuning(kTuneConvTcGroups) : 3;
   a.flush_st = flush_env;
-  a.groups = groups_env > 3 ? 3 : groups_env;
+  a.groups = groups_env > 3 ? 3 : groups_env;              // a fourth group takes the loader warps when TMA feeds grad_output (below)
   a.checked = (a.padH != 0 || a.padW != 0) ? 1 : 0;
   a.vec = (HWo % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_output) & 15) == 0) ? 1 : 0;
   const int nci_max = 127 / KK + 2 < a.C ? 127 / KK + 2 : a.C;
@@ -976,7 +1029,29 @@ int conv2d_wgrad_tc_f32(cudaStream_t st, const am_conv2d_desc& d, int64_t Ho, in
     a.dbg = (long long*)((char*)base + 512);
     AM_CUDA_TRY(cudaMemsetAsync(a.dbg, 0, 16 * sizeof(long long), st));
   }
-  conv_wgrad_tc_kernel<<<a.nchunks * a.nslices, 768, smem, st>>>(a);
+  // pre-split grad_output planes + tensor maps (rows of 16-byte multiples, aligned base); otherwise the loader warps do it
+  CUtensorMap tmG[2];
+  memset(tmG, 0, sizeof(tmG));
+  a.b_tma = 0;
+  int64_t gtotal = 0;
+  if (gout_planes_ok(d, HWo, grad_output, &gtotal)) {
+    void* planes = nullptr;
+    if ((rc = workspace(kWsGoutSplit, (size_t)gtotal * 2 * sizeof(float) + 256, &planes))) return rc;
+    float* ghi = (float*)planes; float* glo = ghi + gtotal;
+    int64_t blocks = ceil_div(gtotal / 4, 256);
+    if (blocks > 16 * (int64_t)sm_count()) blocks = 16 * (int64_t)sm_count();
+    wgrad_split_gout_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float4*)grad_output, (float4*)ghi, (float4*)glo, gtotal / 4);
+    g_launch_count++;
+    AM_CUDA_TRY(cudaGetLastError());
+    const uint64_t dims[3] = {(uint64_t)HWo, (uint64_t)a.CO, (uint64_t)a.N};
+    const uint64_t strides[2] = {(uint64_t)HWo * 4, (uint64_t)HWo * a.CO * 4};
+    const uint32_t box[3] = {32u, (uint32_t)a.NP, 1u};
+    if ((rc = make_tmap_f32_nd_sw128(&tmG[0], ghi, 3, dims, strides, box))) return rc;
+    if ((rc = make_tmap_f32_nd_sw128(&tmG[1], glo, 3, dims, strides, box))) return rc;
+    a.b_tma = 1;
+    if (tuning(kTuneConvTcGroups) == 0 || tuning(kTuneConvTcGroups) == 4) a.groups = 4;
+  }
+  conv_wgrad_tc_kernel<<<a.nchunks * a.nslices, 768, smem, st>>>(tmG[0], tmG[1], a);
   g_launch_count++;
   AM_CUDA_TRY(cudaGetLastError());
   if (a.dbg) {

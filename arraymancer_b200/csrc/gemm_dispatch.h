@@ -26,6 +26,7 @@ enum TuneKey : int {
   kTuneDmmaTma,            // "dmma_tma": TMA-fed 16-warp DMMA kernel for unit-stride float64 operands (default 1; 0: register-staged kernel)
   kTuneConvTcHiRes,        // "convtc_hi_resident": tcgen05 conv forward keeps the hi weight planes resident in shared memory (default 1)
   kTuneConvTcFlushKb,      // "convtc_flush_kb": k blocks (of 32) per TMEM accumulation chain of the tcgen05 conv forward (default 4)
+  kTuneConvTcWgradTma,     // "convtc_wgrad_tma": tcgen05 wgrad fetches grad_output stages by TMA from pre-split hi / lo planes (default 1)
   kTuneCount
 };
 int tuning(int key);

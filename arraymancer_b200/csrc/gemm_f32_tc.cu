@@ -497,6 +497,20 @@ int make_tmap_f32_nd(CUtensorMap* tm, const float* base, int rank, const uint64_
   return AM_OK;
 }
 
+// same, 128-byte swizzle (the box's inner dimension must be 32 floats): lands tiles in the K-major SW128 layout UMMA reads
+int make_tmap_f32_nd_sw128(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box) {
+  if (!gemm_f32_tc_available()) { set_last_error("TMA needs a compute-capability 10.x device"); return AM_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1u; }
+  for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (rank %d, sw128) failed (%d)", rank, (int)r); return AM_ERR_CUDA; }
+  return AM_OK;
+}
+
 // Dense 2-D float64 tensor map (inner dimension first) for the TMA-fed DMMA kernel; zero fill outside the tensor.
 int make_tmap_f64_2d(CUtensorMap* tm, const double* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                      uint32_t box_inner, uint32_t box_outer) {
